@@ -1,0 +1,144 @@
+/*
+ * picovdb_b200 -- C ABI of the B200-native exact cosine top-k engine.
+ *
+ * This header is the drop-in boundary for the one hot path of wensheng/picovdb that this
+ * repository rebuilds: the NumPy branch of PicoVectorDB.query() and the store it scans.
+ * The reference has NO FFI of its own (it is a single pure-Python module), so every entry
+ * point below cites the reference statement(s) it replaces (file:line, relative to the
+ * reference tree); INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - every function returns PVDB_OK (0) or a negative PVDB_ERR_* code; the thread-local
+ *     message of the last failure is available from pvdb_last_error().
+ *   - "host" entry points take host buffers, run on the store's own stream and return when the
+ *     results are in the caller's buffers.  "_dev" entry points take device pointers plus a
+ *     cudaStream_t (passed as void*; NULL is CUDA's legacy default stream) and only enqueue work;
+ *     the library orders them against earlier calls on other streams with an event.
+ *   - matrices are row-major; row indices are int64; outputs are sorted by (score descending,
+ *     row ascending) and padded with score = -inf, row = -1 when fewer than k candidates exist.
+ *   - bitmaps are uint32 words, bit (r & 31) of word (r >> 5) describes row r.
+ *   - a handle serialises its own calls with an internal mutex; device memory is owned by the
+ *     library.  There is no CPU fallback: every call fails with PVDB_ERR_CUDA without a GPU.
+ */
+#ifndef PICOVDB_B200_H
+#define PICOVDB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVDB_ABI_VERSION 1
+
+#define PVDB_OK 0
+#define PVDB_ERR_INVALID (-1)     /* bad argument */
+#define PVDB_ERR_CUDA (-2)        /* CUDA runtime / driver failure (incl. no device) */
+#define PVDB_ERR_OOM (-3)         /* device or pinned allocation failed */
+#define PVDB_ERR_UNSUPPORTED (-4) /* requested precision / layout not available on this store */
+#define PVDB_ERR_CAPACITY (-5)    /* fixed-capacity store is full (pico_vdb.py:441-442) */
+
+/* store flags (pvdb_store_create) */
+#define PVDB_STORE_F32 0x1            /* keep the fp32 matrix (reference layout, pico_vdb.py:136) */
+#define PVDB_STORE_BF16 0x2           /* keep a bf16 mirror of every row */
+#define PVDB_STORE_FIXED_CAPACITY 0x4 /* never grow past reserve_rows (capacity=, pico_vdb.py:286-296) */
+
+/* scoring precision (low byte of the search flags) */
+#define PVDB_PREC_AUTO 0 /* F32 scan for few queries, tensor-core batch path otherwise */
+#define PVDB_PREC_F32 1  /* fp32 CUDA-core scan of the fp32 matrix (exact path) */
+#define PVDB_PREC_TF32 2 /* tcgen05 kind::tf32 over the fp32 matrix, fp32 re-scoring of candidates */
+#define PVDB_PREC_BF16 3 /* bf16 mirror: fp32-accumulated scan (1 query) / tcgen05 kind::f16 (batch) */
+#define PVDB_PREC_MASK 0xff
+/* search flags */
+#define PVDB_SEARCH_QUERIES_NORMALIZED 0x100 /* skip the query L2-normalisation (pico_vdb.py:584-591) */
+#define PVDB_SEARCH_NO_RESCORE 0x200         /* tensor-core paths: return the low-precision scores */
+
+typedef struct pvdb_store pvdb_store_t;
+
+typedef struct pvdb_store_info {
+  int32_t dim;          /* embedding dimension */
+  int32_t ld_f32;       /* row stride of the fp32 matrix, in elements (dim rounded up to 4) */
+  int32_t ld_bf16;      /* row stride of the bf16 mirror, in elements (dim rounded up to 8) */
+  int32_t flags;        /* PVDB_STORE_* */
+  int32_t device;       /* CUDA ordinal */
+  int32_t reserved;
+  int64_t rows;         /* slots in use (high-water mark) == len(_ids) in the reference */
+  int64_t capacity;     /* slots allocated on the device */
+  int64_t active;       /* rows whose active bit is set == len(_id2idx) */
+  int64_t row_base;     /* added to every row index written by a search (shard offset) */
+  uint64_t device_bytes; /* bytes of HBM held by this store */
+} pvdb_store_info_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int pvdb_abi_version(void);
+/* message of the last failing call on this thread ("" if none) */
+const char* pvdb_last_error(void);
+/* number of visible CUDA devices; PVDB_ERR_CUDA if the runtime cannot initialise */
+int pvdb_device_count(int* out_count);
+
+/* ---- store: replaces the `_vectors` matrix + `_active_indices` (pico_vdb.py:136,143) ----- */
+/* Allocate a store on `device` for `dim`-float rows with room for `reserve_rows` rows. */
+int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_t reserve_rows, int flags);
+int pvdb_store_destroy(pvdb_store_t* s);
+/* Grow the allocation to at least `rows` slots (replaces the np.vstack realloc, pico_vdb.py:451-462). */
+int pvdb_store_reserve(pvdb_store_t* s, int64_t rows);
+int pvdb_store_info(pvdb_store_t* s, pvdb_store_info_t* out);
+/* Shard offset added to result rows (multi-GPU row sharding; no reference counterpart). */
+int pvdb_store_set_row_base(pvdb_store_t* s, int64_t row_base);
+
+/* Fused L2-normalise + scatter + set-active: row rows[i] := vecs[i] / ||vecs[i]||, the zero vector
+ * becomes e0 (replaces _normalize + the row write of upsert, pico_vdb.py:58-68, 422, 430, 436,
+ * 451-462, 466-472).  vecs is n x dim dense fp32; rows must be unique within one call; rows past
+ * the current high-water mark extend the store (slots in between stay inactive and zero). */
+int pvdb_store_upsert(pvdb_store_t* s, const float* vecs, const int64_t* rows, int64_t n);
+int pvdb_store_upsert_dev(pvdb_store_t* s, const float* d_vecs, const int64_t* d_rows, int64_t n,
+                          int64_t max_row, void* stream);
+/* Same, for n consecutive rows row0 .. row0+n-1 (bulk ingest; no row array needed). */
+int pvdb_store_upsert_range(pvdb_store_t* s, const float* vecs, int64_t row0, int64_t n);
+int pvdb_store_upsert_range_dev(pvdb_store_t* s, const float* d_vecs, int64_t row0, int64_t n,
+                                void* stream);
+
+/* Clear the active bit and zero-fill the rows (replaces pico_vdb.py:523 + :528-531). */
+int pvdb_store_delete(pvdb_store_t* s, const int64_t* rows, int64_t n);
+
+/* Copy rows out as n x dim dense fp32 (replaces `self._vectors[idx].copy()`, pico_vdb.py:945). */
+int pvdb_store_fetch(pvdb_store_t* s, const int64_t* rows, int64_t n, float* out);
+/* Copy rows row0 .. row0+n-1 out as dense fp32 (feeds np.save in save(), pico_vdb.py:356). */
+int pvdb_store_download(pvdb_store_t* s, int64_t row0, int64_t n, float* out);
+/* Raw load of already-normalised rows (the np.load of _load_or_init, pico_vdb.py:233-237): no
+ * normalisation; `active_bits` has ceil(n/32) words for rows row0.. (row0 % 32 == 0), NULL = all
+ * active (rebuild of _active_indices, pico_vdb.py:247-259). */
+int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const float* vecs,
+                      const uint32_t* active_bits);
+/* Copy the active bitmap out: ceil(rows/32) words. */
+int pvdb_store_active_bits(pvdb_store_t* s, uint32_t* out_words);
+/* Compaction: new row i := old row keep_rows[i] (ascending), all n kept rows active, rows := n
+ * (replaces the fancy-index copy of vacuum(), pico_vdb.py:840-848). */
+int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int64_t n);
+
+/* ---- search: replaces pico_vdb.py:584-591 + :683-714 -------------------------------------- */
+/* For each of nq queries (nq x dim fp32): normalise (zero -> e0) unless flagged, score every row
+ * whose active bit -- and prefilter bit, when prefilter_bits != NULL (ceil(rows/32) words) -- is
+ * set, and write the k best as out_scores[nq*k] / out_rows[nq*k]. */
+int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,
+                const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows);
+int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
+                    const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
+                    int64_t* d_out_rows, void* stream);
+
+/* k-way merge of nlists per-shard results (what an all-gather of the per-GPU outputs produces)
+ * into [nq][k]; rows are global already.  List l's scores start at d_scores + l*scores_stride
+ * (elements) and its rows at d_rows + l*rows_stride; a stride <= 0 means contiguous (nq*k), so one
+ * packed all-gather buffer of {rows, scores} blocks can be merged in place.  Device pointers. */
+int pvdb_merge_topk_dev(int device, const float* d_scores, const int64_t* d_rows, int nlists,
+                        int64_t nq, int k, int64_t scores_stride, int64_t rows_stride,
+                        float* d_out_scores, int64_t* d_out_rows, void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench bookkeeping). */
+int64_t pvdb_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICOVDB_B200_H */

@@ -1,0 +1,171 @@
+// C ABI: search + merge entry points (the read side of the hot path).
+#include <algorithm>
+#include <cstring>
+
+#include "batch.cuh"
+#include "scan.cuh"
+#include "store.cuh"
+
+using namespace pvdb;
+
+namespace pvdb {
+
+__global__ void fill_empty_results_kernel(float* scores, int64_t* rows, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    scores[i] = -INFINITY;
+    rows[i] = -1;
+  }
+}
+
+static int fill_empty(float* d_scores, int64_t* d_rows, int64_t n, cudaStream_t st) {
+  if (n == 0) return PVDB_OK;
+  const int blocks = static_cast<int>(std::min<int64_t>((n + 255) / 256, kNumSMs * 8));
+  fill_empty_results_kernel<<<blocks, 256, 0, st>>>(d_scores, d_rows, n);
+  PVDB_LAUNCH_CHECK();
+  return PVDB_OK;
+}
+
+// Per-query scan passes (exact fp32 accumulation, fp32 matrix or bf16 mirror).  k > kFusedK is
+// served by paging: pass p only admits keys strictly below the last key of pass p-1, which the
+// kernel keeps on the device, so no host round trip separates the passes.
+static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, int64_t nq, int k, const uint32_t* d_pref,
+                       float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+  const int grid = scan_grid_blocks();
+  const size_t list_bytes = static_cast<size_t>(grid) * kFusedK * sizeof(uint64_t);
+  PVDB_TRY(s->d_partial.ensure(list_bytes + 64));
+  unsigned char* ctrl = static_cast<unsigned char*>(s->d_partial.ptr) + list_bytes;
+  if (s->partial_gen_inited != s->d_partial.gen) {
+    PVDB_CUDA(cudaMemsetAsync(ctrl, 0, 64, st));
+    s->partial_gen_inited = s->d_partial.gen;
+  }
+  ScanParams p{};
+  p.matrix = bf16 ? s->bf16.ptr : s->f32.ptr;
+  p.n_rows = s->rows;
+  p.row_chunks = bf16 ? s->ld_bf16 / 8 : s->ld_f32 / 4;
+  p.active = static_cast<const uint32_t*>(s->active.ptr);
+  p.prefilter = d_pref;
+  p.query_floats = s->ldq;
+  p.partial = static_cast<uint64_t*>(s->d_partial.ptr);
+  p.ticket = reinterpret_cast<unsigned int*>(ctrl);
+  p.next_upper = reinterpret_cast<uint64_t*>(ctrl + 8);
+  p.row_base = s->row_base;
+  for (int64_t q = 0; q < nq; ++q) {
+    p.query = d_qn + q * s->ldq;
+    for (int k0 = 0; k0 < k; k0 += kFusedK) {
+      p.k = std::min(kFusedK, k - k0);
+      p.upper = (k0 == 0) ? nullptr : p.next_upper;
+      p.out_scores = d_out_scores + q * k + k0;
+      p.out_rows = d_out_rows + q * k + k0;
+      PVDB_TRY(launch_scan(p, bf16, st));
+    }
+  }
+  return PVDB_OK;
+}
+
+// Device-side search shared by both entry points.  d_queries is nq x dim fp32 (raw).
+static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int k, const uint32_t* d_pref,
+                         int flags, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+  if (nq == 0) return PVDB_OK;
+  int prec = flags & PVDB_PREC_MASK;
+  const bool has_f32 = (s->flags & PVDB_STORE_F32) != 0;
+  const bool has_b16 = (s->flags & PVDB_STORE_BF16) != 0;
+  if (prec == PVDB_PREC_AUTO) {
+    if (nq < kBatchMinQueries || !batch_path_available())
+      prec = has_f32 ? PVDB_PREC_F32 : PVDB_PREC_BF16;
+    else
+      prec = has_f32 ? PVDB_PREC_TF32 : PVDB_PREC_BF16;
+  }
+  if ((prec == PVDB_PREC_F32 || prec == PVDB_PREC_TF32) && !(s->flags & PVDB_STORE_F32))
+    return fail(PVDB_ERR_UNSUPPORTED, "search: this store keeps no fp32 matrix");
+  if (prec == PVDB_PREC_BF16 && !has_b16) return fail(PVDB_ERR_UNSUPPORTED, "search: this store keeps no bf16 mirror");
+  if (prec < PVDB_PREC_F32 || prec > PVDB_PREC_BF16) return fail(PVDB_ERR_INVALID, "search: unknown precision %d", prec);
+  if (s->rows == 0) return fill_empty(d_out_scores, d_out_rows, nq * k, st);
+
+  const bool batch = batch_path_available() && nq >= kBatchMinQueries &&
+                     (prec == PVDB_PREC_TF32 || prec == PVDB_PREC_BF16);
+  const bool normalised = (flags & PVDB_SEARCH_QUERIES_NORMALIZED) != 0;
+  const bool need16 = batch && (prec == PVDB_PREC_BF16);
+  const float* d_qn = nullptr;
+  __nv_bfloat16* d_qn16 = nullptr;
+  if (normalised && s->ldq == s->dim && !need16) {
+    d_qn = d_queries;  // already in the padded layout the kernels read: no preparation launch at all
+  } else {
+    PVDB_TRY(s->d_qn.ensure(static_cast<size_t>(nq) * s->ldq * sizeof(float)));
+    if (need16) {
+      PVDB_TRY(s->d_qn16.ensure(static_cast<size_t>(nq) * s->ldq * sizeof(__nv_bfloat16)));
+      d_qn16 = static_cast<__nv_bfloat16*>(s->d_qn16.ptr);
+    }
+    PVDB_TRY(launch_prepare_queries(d_queries, nq, s->dim, normalised, static_cast<float*>(s->d_qn.ptr), d_qn16,
+                                    s->ldq, st));
+    d_qn = static_cast<const float*>(s->d_qn.ptr);
+  }
+
+  if (batch) {
+    return search_batch(s, prec == PVDB_PREC_BF16, d_qn, d_qn16, nq, k, d_pref, (flags & PVDB_SEARCH_NO_RESCORE) != 0,
+                        d_out_scores, d_out_rows, st);
+  }
+  // scan path: TF32 requests with few queries are served by the exact fp32 scan
+  return search_scan(s, prec == PVDB_PREC_BF16, d_qn, nq, k, d_pref, d_out_scores, d_out_rows, st);
+}
+
+}  // namespace pvdb
+
+#define PVDB_ENTER(s)                                                     \
+  if ((s) == nullptr) return fail(PVDB_ERR_INVALID, "null store handle"); \
+  std::lock_guard<std::mutex> _guard((s)->mu);                            \
+  PVDB_CUDA(cudaSetDevice((s)->device))
+
+extern "C" int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
+                               const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
+                               int64_t* d_out_rows, void* stream) {
+  PVDB_ENTER(s);
+  if (nq < 0 || k < 1 || (nq > 0 && (!d_queries || !d_out_scores || !d_out_rows)))
+    return fail(PVDB_ERR_INVALID, "search_dev: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PVDB_TRY(s->use_stream(st));
+  return search_device(s, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, st);
+}
+
+extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,
+                           const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
+  PVDB_ENTER(s);
+  if (nq < 0 || k < 1 || (nq > 0 && (!queries || !out_scores || !out_rows)))
+    return fail(PVDB_ERR_INVALID, "search: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
+  if (nq == 0) return PVDB_OK;
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  const size_t q_bytes = static_cast<size_t>(nq) * s->dim * sizeof(float);
+  const size_t n_out = static_cast<size_t>(nq) * k;
+  // results: rows (int64) first, then scores (fp32) so both are naturally aligned in one block
+  const size_t out_bytes = n_out * (sizeof(int64_t) + sizeof(float));
+  PVDB_TRY(s->d_in.ensure(q_bytes));
+  PVDB_TRY(s->d_out.ensure(out_bytes));
+  PVDB_TRY(s->h_pinned.ensure(out_bytes));
+  PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, queries, q_bytes, cudaMemcpyHostToDevice, st));
+  const uint32_t* d_pref = nullptr;
+  if (prefilter_bits && s->rows > 0) {
+    const size_t nwords = static_cast<size_t>((s->rows + 31) >> 5);
+    PVDB_TRY(s->d_prefilter.ensure(nwords * sizeof(uint32_t)));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_prefilter.ptr, prefilter_bits, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    d_pref = static_cast<const uint32_t*>(s->d_prefilter.ptr);
+  }
+  int64_t* d_rows = static_cast<int64_t*>(s->d_out.ptr);
+  float* d_scores = reinterpret_cast<float*>(d_rows + n_out);
+  PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_pref, flags, d_scores, d_rows, st));
+  PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  const int64_t* h_rows = static_cast<const int64_t*>(s->h_pinned.ptr);
+  std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
+  std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_merge_topk_dev(int device, const float* d_scores, const int64_t* d_rows, int nlists,
+                                   int64_t nq, int k, int64_t scores_stride, int64_t rows_stride,
+                                   float* d_out_scores, int64_t* d_out_rows, void* stream) {
+  PVDB_CUDA(cudaSetDevice(device));
+  if (!d_scores || !d_rows || !d_out_scores || !d_out_rows) return fail(PVDB_ERR_INVALID, "merge: null buffer");
+  return launch_merge_topk(d_scores, d_rows, nlists, nq, k, scores_stride, rows_stride, d_out_scores, d_out_rows,
+                           static_cast<cudaStream_t>(stream));
+}

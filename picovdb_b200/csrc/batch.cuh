@@ -1,0 +1,20 @@
+// Batched queries: tcgen05 / TMEM tensor-core GEMM with a fused mask + top-k epilogue, followed by
+// an fp32 re-scoring pass (replaces the batched form of picovdb/pico_vdb.py:683-714).
+#pragma once
+
+#include "common.cuh"
+
+struct pvdb_store;
+
+namespace pvdb {
+
+constexpr int64_t kBatchMinQueries = 3;  // fewer queries are cheaper as back-to-back HBM scans
+
+bool batch_path_available();
+
+// d_qn: nq x ldq normalised fp32 queries; d_qn16: the same in bf16 (only for use_bf16).
+int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq, int k,
+                 const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows,
+                 cudaStream_t st);
+
+}  // namespace pvdb

@@ -1,0 +1,40 @@
+// Single-query masked scan + fused top-k ("GEMV path"): the HBM-bound replacement of
+//   scores = q @ V.T ; argpartition ; argsort        (picovdb/pico_vdb.py:683-714)
+#pragma once
+
+#include "common.cuh"
+
+namespace pvdb {
+
+struct ScanParams {
+  const void* matrix;        // fp32 or bf16 row-major matrix
+  int64_t n_rows;            // rows to scan (high-water mark)
+  int row_chunks;            // 16-byte chunks per row (ld * sizeof(T) / 16)
+  const uint32_t* active;    // active bitmap (always present)
+  const uint32_t* prefilter; // optional second bitmap, ANDed with `active`
+  const float* query;        // normalised query, padded with zeros to a multiple of 8 floats
+  int query_floats;          // padded query length
+  int k;                     // 1 .. kFusedK for this pass
+  const uint64_t* upper;     // only keys strictly below *upper qualify (paging); NULL = no bound
+  uint64_t* partial;         // [gridDim.x][k] per-block lists
+  unsigned int* ticket;      // last-block-done counter (self-resetting)
+  uint64_t* next_upper;      // receives the k-th key of this pass (0 when fewer than k found)
+  float* out_scores;         // [k]
+  int64_t* out_rows;         // [k]
+  int64_t row_base;
+};
+
+// Launch one scan pass on `stream`.  `is_bf16` selects the mirror layout.
+int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream);
+int scan_grid_blocks();
+
+// Query preparation (picovdb/pico_vdb.py:584-591): L2-normalise each query in fp32, zero -> e0,
+// write nq x ldq fp32 (zero padded) and optionally a bf16 copy with row stride ldq.
+int launch_prepare_queries(const float* d_raw, int64_t nq, int dim, bool already_normalised, float* d_qn,
+                           __nv_bfloat16* d_qn16, int ldq, cudaStream_t stream);
+
+int launch_merge_topk(const float* d_scores, const int64_t* d_rows, int nlists, int64_t nq, int k,
+                      int64_t scores_stride, int64_t rows_stride, float* d_out_scores, int64_t* d_out_rows,
+                      cudaStream_t stream);
+
+}  // namespace pvdb

@@ -1,0 +1,615 @@
+// Store management + the write-side kernels of the hot path:
+//   fused L2-normalise + scatter + set-active  (reference: _normalize + upsert row write,
+//                                               picovdb/pico_vdb.py:58-68, 413-472)
+//   delete = clear active bit + zero row       (pico_vdb.py:514-531)
+//   row fetch / download / raw upload / compaction (pico_vdb.py:945, 356, 233-259, 840-848)
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "store.cuh"
+
+namespace pvdb {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+// ---------------------------------------------------------------------------- buffers
+int DeviceBuffer::grow(size_t new_bytes, cudaStream_t stream) {
+  if (new_bytes <= bytes) return PVDB_OK;
+  void* np = nullptr;
+  PVDB_CUDA(cudaMalloc(&np, new_bytes));
+  if (bytes) PVDB_CUDA(cudaMemcpyAsync(np, ptr, bytes, cudaMemcpyDeviceToDevice, stream));
+  PVDB_CUDA(cudaMemsetAsync(static_cast<char*>(np) + bytes, 0, new_bytes - bytes, stream));
+  PVDB_CUDA(cudaStreamSynchronize(stream));
+  if (ptr) PVDB_CUDA(cudaFree(ptr));
+  ptr = np;
+  bytes = new_bytes;
+  return PVDB_OK;
+}
+
+void DeviceBuffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+int Scratch::ensure(size_t need) {
+  if (need <= bytes) return PVDB_OK;
+  size_t nb = std::max(need, bytes + bytes / 2);
+  nb = (nb + 255) & ~size_t(255);
+  if (ptr) {
+    // outstanding work may still read the old block: the caller's stream is synchronised by
+    // cudaFree / cudaFreeHost themselves (both are device-synchronising calls).
+    if (pinned_host) PVDB_CUDA(cudaFreeHost(ptr)); else PVDB_CUDA(cudaFree(ptr));
+    ptr = nullptr;
+    bytes = 0;
+  }
+  if (pinned_host) PVDB_CUDA(cudaMallocHost(&ptr, nb)); else PVDB_CUDA(cudaMalloc(&ptr, nb));
+  bytes = nb;
+  ++gen;
+  return PVDB_OK;
+}
+
+void Scratch::release() {
+  if (ptr) { if (pinned_host) cudaFreeHost(ptr); else cudaFree(ptr); }
+  ptr = nullptr;
+  bytes = 0;
+}
+
+// ---------------------------------------------------------------------------- kernels
+// One warp per input vector.  Pass 1: per-lane fp32 partial sums of squares, fp64 warp reduction,
+// norm rounded to fp32 (the reference computes sqrt(dot(x,x)) in fp32 and divides by that fp32
+// value, pico_vdb.py:60-68).  Pass 2: IEEE fp32 division, zero vector -> e0, write the fp32 row,
+// the bf16 mirror row and the pad columns, then set the row's active bit.
+__global__ void __launch_bounds__(256) upsert_normalize_scatter_kernel(
+    const float* __restrict__ src, const int64_t* __restrict__ rows, int64_t row0, int64_t n, int dim,
+    float* __restrict__ f32, int ld32, __nv_bfloat16* __restrict__ b16, int ld16,
+    uint32_t* __restrict__ active) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int ldmax = ld32 > ld16 ? ld32 : ld16;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float* v = src + i * dim;
+    float ss = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+      float x = v[c];
+      ss = fmaf(x, x, ss);
+    }
+    double d = static_cast<double>(ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const float nrm = static_cast<float>(sqrt(d));
+    const bool zero = (nrm == 0.f);
+    const int64_t row = rows ? rows[i] : row0 + i;
+    for (int c = lane; c < ldmax; c += 32) {
+      float y = 0.f;
+      if (c < dim) y = zero ? (c == 0 ? 1.f : 0.f) : __fdiv_rn(v[c], nrm);
+      if (f32 != nullptr && c < ld32) f32[row * ld32 + c] = y;
+      if (b16 != nullptr && c < ld16) b16[row * ld16 + c] = __float2bfloat16_rn(y);
+    }
+    if (lane == 0) atomicOr(&active[row >> 5], 1u << (row & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256) delete_rows_kernel(const int64_t* __restrict__ rows, int64_t n,
+                                                          float* __restrict__ f32, int ld32,
+                                                          __nv_bfloat16* __restrict__ b16, int ld16,
+                                                          uint32_t* __restrict__ active) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t row = rows[i];
+    if (f32) for (int c = lane; c < ld32; c += 32) f32[row * ld32 + c] = 0.f;
+    if (b16) for (int c = lane; c < ld16; c += 32) b16[row * ld16 + c] = __float2bfloat16_rn(0.f);
+    if (lane == 0) atomicAnd(&active[row >> 5], ~(1u << (row & 31)));
+  }
+}
+
+// out[i, :] = row rows[i] (or row0+i) as dense fp32; reads the fp32 matrix when present, else the
+// bf16 mirror.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const int64_t* __restrict__ rows, int64_t row0,
+                                                          int64_t n, int dim,
+                                                          const float* __restrict__ f32, int ld32,
+                                                          const __nv_bfloat16* __restrict__ b16, int ld16,
+                                                          float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t row = rows ? rows[i] : row0 + i;
+    for (int c = lane; c < dim; c += 32)
+      out[i * dim + c] = f32 ? f32[row * ld32 + c] : __bfloat162float(b16[row * ld16 + c]);
+  }
+}
+
+// Rows [row0, row0+n): build the bf16 mirror (and, for a bf16-only store, take the values from
+// the dense staging buffer `src`).
+__global__ void __launch_bounds__(256) mirror_rows_kernel(const float* __restrict__ src_dense, int dim,
+                                                          const float* __restrict__ f32, int ld32,
+                                                          __nv_bfloat16* __restrict__ b16, int ld16,
+                                                          int64_t row0, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t row = row0 + i;
+    for (int c = lane; c < ld16; c += 32) {
+      float y = 0.f;
+      if (c < dim) y = src_dense ? src_dense[i * dim + c] : f32[row * ld32 + c];
+      b16[row * ld16 + c] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// active[w] for the words covering rows [row0, row0+n): take `bits` (word 0 == rows row0..row0+31)
+// or all ones, restricted to the range; bits outside the range keep their value.
+__global__ void set_active_range_kernel(uint32_t* __restrict__ active, int64_t row0, int64_t n,
+                                        const uint32_t* __restrict__ bits) {
+  const int64_t w0 = row0 >> 5;
+  const int64_t w1 = (row0 + n + 31) >> 5;
+  for (int64_t w = w0 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < w1;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t lo = w << 5;
+    uint32_t mask = 0xffffffffu;
+    if (lo < row0) mask &= 0xffffffffu << (row0 - lo);
+    if (lo + 32 > row0 + n) mask &= 0xffffffffu >> (lo + 32 - (row0 + n));
+    const uint32_t val = bits ? bits[w - w0] : 0xffffffffu;
+    active[w] = (active[w] & ~mask) | (val & mask);
+  }
+}
+
+__global__ void popcount_kernel(const uint32_t* __restrict__ words, int64_t nwords,
+                                unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (int64_t w = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; w < nwords;
+       w += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    c += __popc(words[w]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// new row i := old row keep[i] for both matrices
+__global__ void __launch_bounds__(256) compact_rows_kernel(const int64_t* __restrict__ keep, int64_t n,
+                                                           const float* __restrict__ f32_old,
+                                                           float* __restrict__ f32_new, int ld32,
+                                                           const __nv_bfloat16* __restrict__ b16_old,
+                                                           __nv_bfloat16* __restrict__ b16_new, int ld16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const int64_t src = keep[i];
+    if (f32_old) for (int c = lane; c < ld32; c += 32) f32_new[i * ld32 + c] = f32_old[src * ld32 + c];
+    if (b16_old) for (int c = lane; c < ld16; c += 32) b16_new[i * ld16 + c] = b16_old[src * ld16 + c];
+  }
+}
+
+static inline int warp_grid(int64_t n_items) {
+  // 8 warps per block; enough blocks for one warp per item, capped at 16 blocks per SM
+  int64_t blocks = (n_items + 7) / 8;
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(blocks, kNumSMs * 16)));
+}
+
+}  // namespace pvdb
+
+using namespace pvdb;
+
+// ---------------------------------------------------------------------------- store methods
+int pvdb_store::use_stream(cudaStream_t s) {
+  // last_stream is always a live stream (it starts as the store's own); nullptr is CUDA's legacy
+  // default stream, which is just another stream here.
+  if (s != last_stream) {
+    PVDB_CUDA(cudaEventRecord(order_event, last_stream));
+    PVDB_CUDA(cudaStreamWaitEvent(s, order_event, 0));
+    last_stream = s;
+  }
+  return PVDB_OK;
+}
+
+int pvdb_store::ensure_capacity(int64_t need_rows, cudaStream_t s) {
+  if (need_rows <= capacity) return PVDB_OK;
+  if ((flags & PVDB_STORE_FIXED_CAPACITY) && capacity > 0)
+    return fail(PVDB_ERR_CAPACITY, "Database capacity exceeded (%lld > %lld rows)",
+                static_cast<long long>(need_rows), static_cast<long long>(capacity));
+  int64_t cap = std::max<int64_t>(need_rows, capacity + capacity / 2);
+  cap = (cap + 1023) & ~int64_t(1023);
+  if (flags & PVDB_STORE_F32) PVDB_TRY(f32.grow(static_cast<size_t>(cap) * ld_f32 * sizeof(float), s));
+  if (flags & PVDB_STORE_BF16)
+    PVDB_TRY(bf16.grow(static_cast<size_t>(cap) * ld_bf16 * sizeof(__nv_bfloat16), s));
+  PVDB_TRY(active.grow(static_cast<size_t>(cap / 32) * sizeof(uint32_t), s));
+  capacity = cap;
+  return PVDB_OK;
+}
+
+#define PVDB_ENTER(s)                                                         \
+  if ((s) == nullptr) return fail(PVDB_ERR_INVALID, "null store handle");     \
+  std::lock_guard<std::mutex> _guard((s)->mu);                                \
+  PVDB_CUDA(cudaSetDevice((s)->device))
+
+// ---------------------------------------------------------------------------- C ABI: library
+extern "C" int pvdb_abi_version(void) { return PVDB_ABI_VERSION; }
+extern "C" const char* pvdb_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t pvdb_kernel_launches(void) { return g_launches.load(); }
+
+extern "C" int pvdb_device_count(int* out_count) {
+  if (!out_count) return fail(PVDB_ERR_INVALID, "out_count is null");
+  int n = 0;
+  PVDB_CUDA(cudaGetDeviceCount(&n));
+  *out_count = n;
+  return PVDB_OK;
+}
+
+// ---------------------------------------------------------------------------- C ABI: store
+extern "C" int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_t reserve_rows, int flags) {
+  if (!out) return fail(PVDB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (dim <= 0 || dim > 65536) return fail(PVDB_ERR_INVALID, "dim %d out of range [1, 65536]", dim);
+  if (reserve_rows < 0) return fail(PVDB_ERR_INVALID, "reserve_rows < 0");
+  if ((flags & (PVDB_STORE_F32 | PVDB_STORE_BF16)) == 0) flags |= PVDB_STORE_F32;
+  int ndev = 0;
+  PVDB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(PVDB_ERR_INVALID, "device %d not in [0, %d)", device, ndev);
+  PVDB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PVDB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(PVDB_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  pvdb_store* s = new pvdb_store();
+  s->device = device;
+  s->dim = dim;
+  s->ld_f32 = (dim + 3) & ~3;
+  s->ld_bf16 = (dim + 7) & ~7;
+  s->ldq = (dim + 7) & ~7;
+  s->flags = flags;
+  s->h_pinned.pinned_host = true;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->order_event, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(PVDB_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
+  }
+  s->last_stream = s->stream;
+  int rc = PVDB_OK;
+  if (reserve_rows > 0) {
+    int keep = s->flags;
+    s->flags &= ~PVDB_STORE_FIXED_CAPACITY;  // the first allocation is always allowed
+    rc = s->ensure_capacity(reserve_rows, s->stream);
+    s->flags = keep;
+  }
+  if (rc != PVDB_OK) {
+    pvdb_store_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
+  if (!s) return PVDB_OK;
+  cudaSetDevice(s->device);
+  cudaDeviceSynchronize();
+  s->f32.release();
+  s->bf16.release();
+  s->active.release();
+  for (Scratch* sc : {&s->d_in, &s->d_rows, &s->d_prefilter, &s->d_qn, &s->d_qn16, &s->d_partial, &s->d_out,
+                      &s->d_misc, &s->h_pinned})
+    sc->release();
+  if (s->order_event) cudaEventDestroy(s->order_event);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_reserve(pvdb_store_t* s, int64_t rows) {
+  PVDB_ENTER(s);
+  PVDB_TRY(s->use_stream(s->stream));
+  int keep = s->flags;
+  if (s->capacity == 0) s->flags &= ~PVDB_STORE_FIXED_CAPACITY;
+  int rc = s->ensure_capacity(rows, s->stream);
+  s->flags = keep;
+  return rc;
+}
+
+extern "C" int pvdb_store_set_row_base(pvdb_store_t* s, int64_t row_base) {
+  PVDB_ENTER(s);
+  s->row_base = row_base;
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_info(pvdb_store_t* s, pvdb_store_info_t* out) {
+  PVDB_ENTER(s);
+  if (!out) return fail(PVDB_ERR_INVALID, "out is null");
+  PVDB_TRY(s->use_stream(s->stream));
+  unsigned long long act = 0;
+  if (s->rows > 0) {
+    PVDB_TRY(s->d_misc.ensure(sizeof(unsigned long long)));
+    PVDB_CUDA(cudaMemsetAsync(s->d_misc.ptr, 0, sizeof(unsigned long long), s->stream));
+    const int64_t nwords = (s->rows + 31) >> 5;
+    const int blocks = static_cast<int>(std::min<int64_t>((nwords + 255) / 256, kNumSMs * 8));
+    popcount_kernel<<<blocks, 256, 0, s->stream>>>(static_cast<const uint32_t*>(s->active.ptr), nwords,
+                                                  static_cast<unsigned long long*>(s->d_misc.ptr));
+    PVDB_LAUNCH_CHECK();
+    PVDB_CUDA(cudaMemcpyAsync(&act, s->d_misc.ptr, sizeof(act), cudaMemcpyDeviceToHost, s->stream));
+    PVDB_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  out->dim = s->dim;
+  out->ld_f32 = s->ld_f32;
+  out->ld_bf16 = s->ld_bf16;
+  out->flags = s->flags;
+  out->device = s->device;
+  out->reserved = 0;
+  out->rows = s->rows;
+  out->capacity = s->capacity;
+  out->active = static_cast<int64_t>(act);
+  out->row_base = s->row_base;
+  out->device_bytes = s->f32.bytes + s->bf16.bytes + s->active.bytes;
+  return PVDB_OK;
+}
+
+// shared tail of the four upsert entry points: data already on the device
+static int upsert_device(pvdb_store* s, const float* d_vecs, const int64_t* d_rows, int64_t row0, int64_t n,
+                         int64_t max_row, cudaStream_t st) {
+  PVDB_TRY(s->ensure_capacity(max_row + 1, st));
+  upsert_normalize_scatter_kernel<<<warp_grid(n), 256, 0, st>>>(
+      d_vecs, d_rows, row0, n, s->dim, static_cast<float*>(s->f32.ptr), s->ld_f32,
+      static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16, static_cast<uint32_t*>(s->active.ptr));
+  PVDB_LAUNCH_CHECK();
+  s->rows = std::max(s->rows, max_row + 1);
+  return PVDB_OK;
+}
+
+static constexpr int64_t kStageBytes = 64ll << 20;  // host data is staged through HBM in 64 MiB pieces
+
+extern "C" int pvdb_store_upsert(pvdb_store_t* s, const float* vecs, const int64_t* rows, int64_t n) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!vecs || !rows || n < 0) return fail(PVDB_ERR_INVALID, "upsert: null buffer or negative count");
+  int64_t max_row = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    if (rows[i] < 0 || rows[i] > 0xfffffffell) return fail(PVDB_ERR_INVALID, "upsert: row %lld out of range", (long long)rows[i]);
+    max_row = std::max(max_row, rows[i]);
+  }
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->ensure_capacity(max_row + 1, st));
+  const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
+  PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
+  PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(std::min(chunk, n)) * sizeof(int64_t)));
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    const int64_t m = std::min(chunk, n - i0);
+    PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, vecs + i0 * s->dim, static_cast<size_t>(m) * s->dim * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, rows + i0, static_cast<size_t>(m) * sizeof(int64_t),
+                              cudaMemcpyHostToDevice, st));
+    PVDB_TRY(upsert_device(s, static_cast<const float*>(s->d_in.ptr), static_cast<const int64_t*>(s->d_rows.ptr),
+                           0, m, max_row, st));
+  }
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_upsert_range(pvdb_store_t* s, const float* vecs, int64_t row0, int64_t n) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!vecs || n < 0 || row0 < 0 || row0 + n - 1 > 0xfffffffell)
+    return fail(PVDB_ERR_INVALID, "upsert_range: bad arguments");
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->ensure_capacity(row0 + n, st));
+  const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
+  PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    const int64_t m = std::min(chunk, n - i0);
+    PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, vecs + i0 * s->dim, static_cast<size_t>(m) * s->dim * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+    PVDB_TRY(upsert_device(s, static_cast<const float*>(s->d_in.ptr), nullptr, row0 + i0, m, row0 + i0 + m - 1, st));
+  }
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_upsert_dev(pvdb_store_t* s, const float* d_vecs, const int64_t* d_rows, int64_t n,
+                                     int64_t max_row, void* stream) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!d_vecs || !d_rows || n < 0 || max_row < 0 || max_row > 0xfffffffell)
+    return fail(PVDB_ERR_INVALID, "upsert_dev: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PVDB_TRY(s->use_stream(st));
+  return upsert_device(s, d_vecs, d_rows, 0, n, max_row, st);
+}
+
+extern "C" int pvdb_store_upsert_range_dev(pvdb_store_t* s, const float* d_vecs, int64_t row0, int64_t n,
+                                           void* stream) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!d_vecs || n < 0 || row0 < 0 || row0 + n - 1 > 0xfffffffell)
+    return fail(PVDB_ERR_INVALID, "upsert_range_dev: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PVDB_TRY(s->use_stream(st));
+  return upsert_device(s, d_vecs, nullptr, row0, n, row0 + n - 1, st);
+}
+
+extern "C" int pvdb_store_delete(pvdb_store_t* s, const int64_t* rows, int64_t n) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!rows || n < 0) return fail(PVDB_ERR_INVALID, "delete: null rows or negative count");
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= s->rows)
+      return fail(PVDB_ERR_INVALID, "delete: row %lld outside [0, %lld)", (long long)rows[i], (long long)s->rows);
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(n) * sizeof(int64_t)));
+  PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, rows, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  delete_rows_kernel<<<warp_grid(n), 256, 0, st>>>(static_cast<const int64_t*>(s->d_rows.ptr), n,
+                                                   static_cast<float*>(s->f32.ptr), s->ld_f32,
+                                                   static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16,
+                                                   static_cast<uint32_t*>(s->active.ptr));
+  PVDB_LAUNCH_CHECK();
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_fetch(pvdb_store_t* s, const int64_t* rows, int64_t n, float* out) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!rows || !out || n < 0) return fail(PVDB_ERR_INVALID, "fetch: null buffer or negative count");
+  for (int64_t i = 0; i < n; ++i)
+    if (rows[i] < 0 || rows[i] >= s->rows)
+      return fail(PVDB_ERR_INVALID, "fetch: row %lld outside [0, %lld)", (long long)rows[i], (long long)s->rows);
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
+  PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
+  PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(std::min(chunk, n)) * sizeof(int64_t)));
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    const int64_t m = std::min(chunk, n - i0);
+    PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, rows + i0, static_cast<size_t>(m) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<warp_grid(m), 256, 0, st>>>(static_cast<const int64_t*>(s->d_rows.ptr), 0, m, s->dim,
+                                                     static_cast<const float*>(s->f32.ptr), s->ld_f32,
+                                                     static_cast<const __nv_bfloat16*>(s->bf16.ptr), s->ld_bf16,
+                                                     static_cast<float*>(s->d_in.ptr));
+    PVDB_LAUNCH_CHECK();
+    PVDB_CUDA(cudaMemcpyAsync(out + i0 * s->dim, s->d_in.ptr, static_cast<size_t>(m) * s->dim * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+  }
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_download(pvdb_store_t* s, int64_t row0, int64_t n, float* out) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!out || n < 0 || row0 < 0 || row0 + n > s->rows)
+    return fail(PVDB_ERR_INVALID, "download: range [%lld, %lld) outside [0, %lld)", (long long)row0,
+                (long long)(row0 + n), (long long)s->rows);
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  if (s->f32.ptr) {
+    const float* src = static_cast<const float*>(s->f32.ptr) + row0 * s->ld_f32;
+    PVDB_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(s->dim) * 4, src, static_cast<size_t>(s->ld_f32) * 4,
+                                static_cast<size_t>(s->dim) * 4, static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
+  } else {
+    const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
+    PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
+    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+      const int64_t m = std::min(chunk, n - i0);
+      gather_rows_kernel<<<warp_grid(m), 256, 0, st>>>(nullptr, row0 + i0, m, s->dim, nullptr, s->ld_f32,
+                                                       static_cast<const __nv_bfloat16*>(s->bf16.ptr), s->ld_bf16,
+                                                       static_cast<float*>(s->d_in.ptr));
+      PVDB_LAUNCH_CHECK();
+      PVDB_CUDA(cudaMemcpyAsync(out + i0 * s->dim, s->d_in.ptr, static_cast<size_t>(m) * s->dim * sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+    }
+  }
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const float* vecs,
+                                 const uint32_t* active_bits) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!vecs || n < 0 || row0 < 0 || row0 + n - 1 > 0xfffffffell)
+    return fail(PVDB_ERR_INVALID, "upload: bad arguments");
+  if (active_bits && (row0 & 31)) return fail(PVDB_ERR_INVALID, "upload: row0 must be a multiple of 32 with active_bits");
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->ensure_capacity(row0 + n, st));
+  const int64_t chunk = std::max<int64_t>(32, (kStageBytes / (static_cast<int64_t>(s->dim) * 4)) & ~int64_t(31));
+  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
+    const int64_t m = std::min(chunk, n - i0);
+    const float* src = vecs + i0 * s->dim;
+    const float* dense = nullptr;
+    if (s->f32.ptr) {
+      float* dst = static_cast<float*>(s->f32.ptr) + (row0 + i0) * s->ld_f32;
+      PVDB_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(s->ld_f32) * 4, src, static_cast<size_t>(s->dim) * 4,
+                                  static_cast<size_t>(s->dim) * 4, static_cast<size_t>(m), cudaMemcpyHostToDevice, st));
+    } else {
+      PVDB_TRY(s->d_in.ensure(static_cast<size_t>(m) * s->dim * sizeof(float)));
+      PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, src, static_cast<size_t>(m) * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+      dense = static_cast<const float*>(s->d_in.ptr);
+    }
+    if (s->bf16.ptr) {
+      mirror_rows_kernel<<<warp_grid(m), 256, 0, st>>>(dense, s->dim, static_cast<const float*>(s->f32.ptr), s->ld_f32,
+                                                       static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16, row0 + i0, m);
+      PVDB_LAUNCH_CHECK();
+    }
+  }
+  const uint32_t* d_bits = nullptr;
+  if (active_bits) {
+    const size_t nwords = static_cast<size_t>((n + 31) >> 5);
+    PVDB_TRY(s->d_prefilter.ensure(nwords * sizeof(uint32_t)));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_prefilter.ptr, active_bits, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    d_bits = static_cast<const uint32_t*>(s->d_prefilter.ptr);
+  }
+  {
+    const int64_t nwords = ((row0 + n + 31) >> 5) - (row0 >> 5);
+    const int blocks = static_cast<int>(std::min<int64_t>((nwords + 255) / 256, kNumSMs * 8));
+    set_active_range_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(s->active.ptr), row0, n, d_bits);
+    PVDB_LAUNCH_CHECK();
+  }
+  s->rows = std::max(s->rows, row0 + n);
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_active_bits(pvdb_store_t* s, uint32_t* out_words) {
+  PVDB_ENTER(s);
+  if (s->rows == 0) return PVDB_OK;
+  if (!out_words) return fail(PVDB_ERR_INVALID, "out_words is null");
+  PVDB_TRY(s->use_stream(s->stream));
+  PVDB_CUDA(cudaMemcpyAsync(out_words, s->active.ptr, static_cast<size_t>((s->rows + 31) >> 5) * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+  PVDB_CUDA(cudaStreamSynchronize(s->stream));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int64_t n) {
+  PVDB_ENTER(s);
+  if (n < 0 || (n > 0 && !keep_rows)) return fail(PVDB_ERR_INVALID, "compact: bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    if (keep_rows[i] < 0 || keep_rows[i] >= s->rows || (i > 0 && keep_rows[i] <= keep_rows[i - 1]))
+      return fail(PVDB_ERR_INVALID, "compact: keep_rows must be strictly ascending rows of the store");
+  }
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  DeviceBuffer nf32, nb16;
+  if (s->capacity > 0) {
+    if (s->f32.ptr) PVDB_TRY(nf32.grow(s->f32.bytes, st));
+    if (s->bf16.ptr) {
+      int rc = nb16.grow(s->bf16.bytes, st);
+      if (rc != PVDB_OK) { nf32.release(); return rc; }
+    }
+  }
+  if (n > 0) {
+    PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(n) * sizeof(int64_t)));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, keep_rows, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    compact_rows_kernel<<<warp_grid(n), 256, 0, st>>>(
+        static_cast<const int64_t*>(s->d_rows.ptr), n, static_cast<const float*>(s->f32.ptr),
+        static_cast<float*>(nf32.ptr), s->ld_f32, static_cast<const __nv_bfloat16*>(s->bf16.ptr),
+        static_cast<__nv_bfloat16*>(nb16.ptr), s->ld_bf16);
+    PVDB_LAUNCH_CHECK();
+  }
+  if (s->active.ptr) {
+    PVDB_CUDA(cudaMemsetAsync(s->active.ptr, 0, s->active.bytes, st));
+    if (n > 0) {
+      const int64_t nwords = (n + 31) >> 5;
+      const int blocks = static_cast<int>(std::min<int64_t>((nwords + 255) / 256, kNumSMs * 8));
+      set_active_range_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(s->active.ptr), 0, n, nullptr);
+      PVDB_LAUNCH_CHECK();
+    }
+  }
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  std::swap(s->f32, nf32);
+  std::swap(s->bf16, nb16);
+  nf32.release();
+  nb16.release();
+  s->rows = n;
+  return PVDB_OK;
+}

@@ -1,0 +1,66 @@
+// Device-resident vector store: the B200 replacement of the reference's `_vectors` matrix and
+// `_active_indices` array (picovdb/pico_vdb.py:136,143).
+#pragma once
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace pvdb {
+
+// One growable device allocation.  Growth keeps the contents and zero-fills the new tail.
+struct DeviceBuffer {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int grow(size_t new_bytes, cudaStream_t stream);  // no-op when new_bytes <= bytes
+  void release();
+};
+
+// Scratch that grows on demand and is reused between calls (never shrinks).
+struct Scratch {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool pinned_host = false;
+  uint64_t gen = 0;  // bumped on every (re)allocation
+  int ensure(size_t need);
+  void release();
+};
+
+}  // namespace pvdb
+
+struct pvdb_store {
+  int device = 0;
+  int dim = 0;
+  int ld_f32 = 0;   // fp32 row stride in elements (multiple of 4 -> 16-byte aligned rows)
+  int ld_bf16 = 0;  // bf16 row stride in elements (multiple of 8 -> 16-byte aligned rows)
+  int ldq = 0;      // padded query length in floats (multiple of 8, zero padded)
+  int flags = 0;
+  int64_t rows = 0;      // high-water mark of slots in use
+  int64_t capacity = 0;  // slots allocated (multiple of 1024)
+  int64_t row_base = 0;
+
+  pvdb::DeviceBuffer f32;     // capacity x ld_f32 floats, pad columns are zero
+  pvdb::DeviceBuffer bf16;    // capacity x ld_bf16 bf16, pad columns are zero
+  pvdb::DeviceBuffer active;  // capacity/32 words
+
+  cudaStream_t stream = nullptr;       // the store's own stream (host entry points)
+  cudaStream_t last_stream = nullptr;  // stream of the most recent call (cross-stream ordering)
+  cudaEvent_t order_event = nullptr;
+  std::mutex mu;
+
+  // per-call scratch (guarded by mu)
+  pvdb::Scratch d_in;       // staged host inputs (vectors / queries)
+  pvdb::Scratch d_rows;     // staged row indices
+  pvdb::Scratch d_prefilter;
+  pvdb::Scratch d_qn;       // normalised queries, nq x ldq fp32
+  pvdb::Scratch d_qn16;     // normalised queries in bf16 (tensor path)
+  pvdb::Scratch d_partial;  // per-block candidate lists + scan control words
+  pvdb::Scratch d_out;      // results before the D2H copy
+  pvdb::Scratch d_misc;
+  pvdb::Scratch h_pinned;   // pinned bounce buffer for results
+  uint64_t partial_gen_inited = 0;  // d_partial.gen whose control words have been zeroed
+
+  // Make `s` the stream the store's data is ordered on (inserts an event edge when it changes).
+  int use_stream(cudaStream_t s);
+  int ensure_capacity(int64_t need_rows, cudaStream_t s);
+};

@@ -1,0 +1,743 @@
+"""``PicoVectorDB`` -- drop-in for wensheng/picovdb's class with the exact-search hot path on a B200.
+
+Level-1 boundary of SURVEY.md 8(b): same constructor, methods, record schema (``_id_`` /
+``_vector_`` / ``_metrics_``), error messages and storage files as the reference class
+(picovdb/pico_vdb.py:97-1011), so user code, the reference's bench scripts and its tests run
+against it unchanged.  What differs is where the numbers live and who computes them:
+
+* the ``_vectors`` matrix and the active-row set are device resident (``DeviceStore``); ``upsert``
+  stages the raw vectors once and a fused CUDA kernel normalises + scatters them
+  (replaces pico_vdb.py:58-68, 422-472);
+* ``query`` builds a row bitmap from ``ids`` / ``where`` (the reference's candidate builder,
+  pico_vdb.py:604-658), hands raw queries + bitmap to ONE C-ABI call and assembles dict results
+  from the returned ``(scores, rows)`` (pico_vdb.py:753-775).  Normalisation, scoring and top-k
+  (pico_vdb.py:584-591, 683-714) all run on the GPU;
+* host bookkeeping (``_ids`` / ``_docs`` / ``_id2idx`` / ``_free`` / ``_active_indices``), the RW
+  lock, persistence format and the quirks listed in SURVEY.md (Q2, Q6, Q7, Q8) are kept.
+
+There is no CPU compute path: constructing a DB without the CUDA extension or without a GPU
+raises.  The FAISS/HNSW keyword arguments are accepted and ignored (approximate search is out of
+scope; the class behaves like the reference with ``no_faiss=True``).
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import logging
+import os
+import threading
+import time
+import warnings
+from contextlib import contextmanager
+from typing import Any, Callable, Literal, Optional, Union
+
+import numpy as np
+
+Float = np.float32
+ADAPTIVE_BUFFER = 32
+ARGSORT_THRESHOLD = 0.2
+K_ID = "_id_"
+K_VECTOR = "_vector_"
+K_METRICS = "_metrics_"
+_HAS_FAISS = False  # the exact path never uses FAISS
+
+logger = logging.getLogger("picovdb")
+
+WhereT = Union[dict[str, Any], Callable[[dict[str, Any]], bool]]
+
+
+# --------------------------------------------------------------------------- small helpers
+def _ids_path(base: str) -> str:
+    return f"{base}.ids.json"
+
+
+def _meta_path(base: str) -> str:
+    return f"{base}.meta.json"
+
+
+def _vecs_path(base: str) -> str:
+    return f"{base}.vecs.npy"
+
+
+def _hash_vec(v: np.ndarray) -> str:
+    return hashlib.md5(v.tobytes()).hexdigest()
+
+
+def _normalize(v: np.ndarray) -> np.ndarray:
+    """Host-side L2 normalisation (zero -> e0).  Used only to derive the md5 auto-id of a record
+    without ``_id_`` so ids stay bit-compatible with the reference; the stored row is
+    normalised by the device kernel."""
+    vec = np.asarray(v, dtype=Float)
+    n = float(np.linalg.norm(vec))
+    if n == 0.0:
+        unit = np.zeros_like(vec, dtype=Float)
+        if unit.size:
+            unit.flat[0] = Float(1.0)
+        return unit
+    return (vec / n).astype(Float, copy=False)
+
+
+def _to_c_f32(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=Float)
+
+
+def _timed(name: str):
+    """DEBUG-level wall-clock logging, same message shape as the reference's decorator."""
+
+    def decorator(func):
+        def wrapper(*args, **kwargs):
+            t0 = time.perf_counter()
+            try:
+                return func(*args, **kwargs)
+            finally:
+                logger.debug("%s took %.4f ms", name, (time.perf_counter() - t0) * 1000)
+
+        wrapper.__name__ = getattr(func, "__name__", name)
+        wrapper.__doc__ = func.__doc__
+        return wrapper
+
+    return decorator
+
+
+class _RWLock:
+    """Writer-exclusive / multi-reader lock (same contract as pico_vdb.py:1019-1063)."""
+
+    def __init__(self) -> None:
+        self._cond = threading.Condition(threading.Lock())
+        self._readers = 0
+        self._writer = False
+
+    def acquire_read(self) -> None:
+        with self._cond:
+            self._cond.wait_for(lambda: not self._writer)
+            self._readers += 1
+
+    def release_read(self) -> None:
+        with self._cond:
+            self._readers -= 1
+            if self._readers == 0:
+                self._cond.notify_all()
+
+    def acquire_write(self) -> None:
+        with self._cond:
+            self._cond.wait_for(lambda: not self._writer and self._readers == 0)
+            self._writer = True
+
+    def release_write(self) -> None:
+        with self._cond:
+            self._writer = False
+            self._cond.notify_all()
+
+    @contextmanager
+    def read_lock(self):
+        self.acquire_read()
+        try:
+            yield
+        finally:
+            self.release_read()
+
+    @contextmanager
+    def write_lock(self):
+        self.acquire_write()
+        try:
+            yield
+        finally:
+            self.release_write()
+
+
+def _default_engine_factory(dim: int, **kw):
+    """The product engine: CUDA or nothing."""
+    from .engine import DeviceStore
+
+    return DeviceStore(dim, **kw)
+
+
+# --------------------------------------------------------------------------- the class
+class PicoVectorDB:
+    """Cosine-only vector DB with metadata persistence; exact search runs on a B200."""
+
+    # Tests that exercise only the host logic replace this with a test-local engine
+    # (tests/_host_engine.py).  The product never does.
+    _engine_factory = staticmethod(_default_engine_factory)
+
+    def __init__(
+        self,
+        embedding_dim: int = 1024,
+        metric: Literal["cosine"] = "cosine",
+        storage_file: str = "picovdb",
+        use_memmap: bool = False,
+        capacity: Optional[int] = None,
+        no_faiss: bool = False,
+        faiss_threads: Optional[int] = None,
+        hnsw_m: Optional[int] = None,
+        hnsw_ef_construction: Optional[int] = None,
+        ef_search_default: Optional[int] = None,
+        hnsw_ef_search_default: Optional[int] = None,
+        faiss_incremental_threshold_ratio: float = 0.2,
+        adaptive_buffer: Optional[int] = None,
+        argsort_threshold: Optional[float] = None,
+        # ---- B200 engine options (no reference counterpart) ----
+        device: Optional[int] = None,
+        bf16_mirror: bool = False,
+        keep_f32: bool = True,
+        precision: str = "auto",
+    ) -> None:
+        self._rwlock = _RWLock()
+        self.dim = int(embedding_dim)
+        self.metric = metric
+        self._path = storage_file
+        self._use_memmap = use_memmap
+        self._capacity = capacity
+        self._precision = precision
+
+        self._ids: list[Any] = []
+        self._docs: list[Optional[dict[str, Any]]] = []
+        self._free: list[int] = []
+        self._id2idx: dict[Any, int] = {}
+        self._additional: dict[str, Any] = {}
+        self._active_indices: np.ndarray = np.empty(0, dtype=np.int64)
+
+        ab_env = os.getenv("PICOVDB_ADAPTIVE_BUFFER")
+        thr_env = os.getenv("PICOVDB_ARGSORT_THRESHOLD")
+        if adaptive_buffer is not None:
+            self._adaptive_buffer = int(adaptive_buffer)
+        else:
+            self._adaptive_buffer = int(ab_env) if ab_env is not None else ADAPTIVE_BUFFER
+        if argsort_threshold is not None:
+            self._argsort_threshold = float(argsort_threshold)
+        else:
+            self._argsort_threshold = float(thr_env) if thr_env is not None else ARGSORT_THRESHOLD
+        self._last_topk_strategy: Optional[str] = None
+        self._last_k_eff: Optional[int] = None
+
+        # HNSW knobs are accepted for signature compatibility and recorded, nothing else
+        self._hnsw_m = int(hnsw_m) if hnsw_m is not None else 32
+        self._hnsw_efc = int(hnsw_ef_construction) if hnsw_ef_construction is not None else 40
+        if hnsw_ef_search_default is not None:
+            self._faiss_ef_search = int(hnsw_ef_search_default)
+        elif ef_search_default is not None:
+            self._faiss_ef_search = int(ef_search_default)
+        else:
+            self._faiss_ef_search = 32
+        self._faiss_incr_threshold_ratio = float(faiss_incremental_threshold_ratio)
+        self._faiss = None
+        self._dirty = False
+
+        if device is None:
+            device = int(os.getenv("PICOVDB_DEVICE", "0"))
+        self._device = device
+        self._engine = type(self)._engine_factory(
+            self.dim,
+            device=device,
+            reserve_rows=int(capacity) if capacity else 0,
+            keep_f32=keep_f32,
+            bf16_mirror=bf16_mirror,
+            fixed_capacity=capacity is not None,
+        )
+        self._host_cache: Optional[np.ndarray] = None  # lazily downloaded copy behind `_vectors`
+        self._load_or_init()
+
+    # ------------------------------------------------------------------ host mirror of the matrix
+    @property
+    def _vectors(self) -> np.ndarray:
+        """Host copy of the device matrix, (rows, dim) C-contiguous fp32 (downloaded on demand)."""
+        if self._host_cache is None:
+            n = len(self._ids)
+            self._host_cache = (
+                self._engine.download(0, n) if n else np.empty((0, self.dim), dtype=Float)
+            )
+        return self._host_cache
+
+    def _invalidate(self) -> None:
+        self._host_cache = None
+
+    # ------------------------------------------------------------------ persistence
+    @_timed("load")
+    def _load_or_init(self) -> None:
+        ids_file, vecs_file, meta_file = _ids_path(self._path), _vecs_path(self._path), _meta_path(self._path)
+        if os.path.exists(ids_file) and os.path.exists(vecs_file):
+            logger.info("Loading existing DB …")
+            with open(ids_file, "r", encoding="utf-8") as f:
+                self._ids = json.load(f)
+            count = len(self._ids)
+            vectors = self._read_vectors(vecs_file, count)
+            if os.path.exists(meta_file):
+                with open(meta_file, "r", encoding="utf-8") as f:
+                    meta_json = json.load(f)
+                self._docs = meta_json.get("data", [None] * count)
+                self._additional = meta_json.get("additional_data", {})
+            else:
+                self._docs = [None] * count
+            active = np.zeros(count, dtype=bool)
+            for i, (_id, doc) in enumerate(zip(self._ids, self._docs)):
+                if doc is None:
+                    self._free.append(i)
+                elif _id is not None:
+                    self._id2idx[_id] = i
+            if self._id2idx:
+                self._active_indices = np.fromiter(self._id2idx.values(), dtype=np.int64)
+                active[self._active_indices] = True
+            if count:
+                self._engine.upload(vectors, 0, active)
+            logger.info("Loaded %d active / %d total vectors", len(self._id2idx), count)
+        else:
+            if self._capacity is not None:
+                cap = int(self._capacity)
+                self._ids = [None] * cap
+                self._docs = [None] * cap
+                self._free = list(range(cap))
+                if self._use_memmap:
+                    # keep the reference's observable side effect: a pre-sized raw file
+                    np.memmap(vecs_file, dtype=Float, mode="w+", shape=(cap, self.dim)).flush()
+            logger.info("No persisted data – fresh DB")
+
+    def _read_vectors(self, vecs_file: str, count: int) -> np.ndarray:
+        try:
+            arr = np.load(vecs_file)
+        except (ValueError, OSError):
+            # headerless pre-allocated file written by `capacity=` + `use_memmap=True`
+            arr = np.fromfile(vecs_file, dtype=Float)
+            if arr.size != count * self.dim:
+                raise
+            arr = arr.reshape(count, self.dim)
+        arr = _to_c_f32(arr)
+        if arr.shape != (count, self.dim):
+            raise ValueError(
+                f"stored matrix has shape {arr.shape}, expected ({count}, {self.dim})"
+            )
+        return arr
+
+    @_timed("save")
+    def save(self) -> None:
+        """Persist atomically: temp files first, then ``os.replace`` (pico_vdb.py:330-393)."""
+        with self._rwlock.write_lock():
+            ids_file, vecs_file, meta_file = _ids_path(self._path), _vecs_path(self._path), _meta_path(self._path)
+            tmp_ids = f"{ids_file}.tmp"
+            tmp_vecs_base = f"{self._path}.vecs.tmp"
+            tmp_vecs = f"{tmp_vecs_base}.npy"
+            tmp_meta = f"{meta_file}.tmp"
+            try:
+                with open(tmp_ids, "w", encoding="utf-8") as f:
+                    json.dump(self._ids, f, ensure_ascii=False)
+                np.save(tmp_vecs_base, self._vectors)
+                with open(tmp_meta, "w", encoding="utf-8") as f:
+                    json.dump(
+                        {"embedding_dim": self.dim, "data": self._docs, "additional_data": self._additional},
+                        f,
+                        ensure_ascii=False,
+                    )
+                os.replace(tmp_ids, ids_file)
+                os.replace(tmp_vecs, vecs_file)
+                os.replace(tmp_meta, meta_file)
+                logger.info("Saved %d vectors", len(self._ids))
+            finally:
+                for tmp in (tmp_ids, tmp_vecs, tmp_meta):
+                    if os.path.exists(tmp):
+                        try:
+                            os.remove(tmp)
+                        except OSError:
+                            pass
+
+    def flush(self) -> None:
+        """No-op: the store is device resident; ``save()`` writes the files."""
+        with self._rwlock.read_lock():
+            return None
+
+    # ------------------------------------------------------------------ counters
+    def size(self) -> int:
+        warnings.warn(
+            "size() is deprecated: use count() for active items; capacity() will be added in a future release.",
+            DeprecationWarning,
+            stacklevel=2,
+        )
+        with self._rwlock.read_lock():
+            return len(self._ids)
+
+    def capacity(self) -> int:
+        with self._rwlock.read_lock():
+            return len(self._ids)
+
+    def count(self) -> int:
+        with self._rwlock.read_lock():
+            return len(self._id2idx)
+
+    def __len__(self) -> int:
+        with self._rwlock.read_lock():
+            return len(self._id2idx)
+
+    # ------------------------------------------------------------------ mutators
+    def upsert(self, items: list[dict[str, Any]]) -> dict[str, list[Any]]:
+        """Insert or update records.  Host side: validation, id / slot bookkeeping, staging of the
+        raw vectors.  Device side (one call): normalise, scatter, set active bits."""
+        with self._rwlock.write_lock():
+            report: dict[str, list[Any]] = {"update": [], "insert": []}
+            staged: list[np.ndarray] = []
+            staged_rows: list[int] = []
+            slot_of_row: dict[int, int] = {}  # a row written twice in one call keeps the last vector
+            appended_ids: list[Any] = []
+            appended_docs: list[dict[str, Any]] = []
+            new_active: list[int] = []
+            try:
+                for item in items:
+                    raw = np.ascontiguousarray(item[K_VECTOR], dtype=Float)
+                    if raw.ndim != 1:
+                        raise ValueError(
+                            f"upsert vector must be 1D with length {self.dim}; got shape {tuple(raw.shape)}"
+                        )
+                    if raw.shape[0] != self.dim:
+                        raise ValueError(
+                            f"upsert vector dim mismatch: expected {self.dim}, got {raw.shape[0]}"
+                        )
+                    meta = {k: v for k, v in item.items() if k != K_VECTOR}
+                    item_id = meta.get(K_ID)
+                    if item_id is None:
+                        item_id = _hash_vec(_normalize(raw))
+                    meta[K_ID] = item_id
+                    if item_id in self._id2idx:
+                        row = self._id2idx[item_id]
+                        if row < len(self._docs):
+                            self._docs[row] = meta
+                        else:
+                            appended_docs[row - len(self._docs)] = meta
+                        report["update"].append(item_id)
+                    else:
+                        if self._free:
+                            row = self._free.pop()
+                            self._ids[row] = item_id
+                            self._docs[row] = meta
+                        else:
+                            if self._capacity is not None:
+                                raise ValueError("Database capacity exceeded")
+                            appended_ids.append(item_id)
+                            appended_docs.append(meta)
+                            row = len(self._ids) + len(appended_ids) - 1
+                        new_active.append(row)
+                        self._id2idx[item_id] = row
+                        report["insert"].append(item_id)
+                    pos = slot_of_row.get(row)
+                    if pos is None:
+                        slot_of_row[row] = len(staged)
+                        staged.append(raw)
+                        staged_rows.append(row)
+                    else:
+                        staged[pos] = raw
+            finally:
+                # whatever was accepted before a validation error is committed, as in the reference
+                # (its row writes happen item by item, pico_vdb.py:428-449)
+                if appended_ids:
+                    self._ids.extend(appended_ids)
+                    self._docs.extend(appended_docs)
+                if staged:
+                    self._engine.upsert_rows(np.stack(staged), np.asarray(staged_rows, dtype=np.int64))
+                    self._invalidate()
+                if new_active:
+                    add = np.asarray(new_active, dtype=np.int64)
+                    self._active_indices = (
+                        np.append(self._active_indices, add) if self._active_indices.size else add
+                    )
+            return report
+
+    def upsert_array(
+        self,
+        vectors: np.ndarray,
+        ids: Optional[list[Any]] = None,
+        docs: Optional[list[dict[str, Any]]] = None,
+    ) -> list[Any]:
+        """Bulk ingest of NEW records from an (n, dim) array: one staging copy, one device call,
+        no per-item numpy work.  ``ids`` default to consecutive integers continuing from the
+        current slot count; every id must be absent from the DB.  Returns the ids."""
+        vecs = _to_c_f32(vectors)
+        if vecs.ndim != 2 or vecs.shape[1] != self.dim:
+            raise ValueError(f"upsert_array expects shape (n, {self.dim}); got {tuple(vecs.shape)}")
+        n = vecs.shape[0]
+        with self._rwlock.write_lock():
+            if self._capacity is not None or self._free:
+                raise ValueError("upsert_array appends rows; it needs a DB without free slots or fixed capacity")
+            row0 = len(self._ids)
+            new_ids = list(range(row0, row0 + n)) if ids is None else list(ids)
+            if len(new_ids) != n or (docs is not None and len(docs) != n):
+                raise ValueError("ids / docs length does not match the number of vectors")
+            if len(set(new_ids)) != n or any(i in self._id2idx for i in new_ids):
+                raise ValueError("upsert_array ids must be unique and not present in the DB")
+            self._engine.upsert_range(vecs, row0)
+            self._invalidate()
+            self._ids.extend(new_ids)
+            if docs is None:
+                self._docs.extend({K_ID: i} for i in new_ids)
+            else:
+                self._docs.extend({**d, K_ID: i} for d, i in zip(docs, new_ids))
+            self._id2idx.update(zip(new_ids, range(row0, row0 + n)))
+            add = np.arange(row0, row0 + n, dtype=np.int64)
+            self._active_indices = np.append(self._active_indices, add) if self._active_indices.size else add
+            return new_ids
+
+    def store_additional_data(self, **kwargs) -> None:
+        with self._rwlock.write_lock():
+            self._additional.update(kwargs)
+
+    def get_additional_data(self) -> dict[str, Any]:
+        with self._rwlock.read_lock():
+            return self._additional
+
+    def delete(self, ids: list[Any]) -> list[Any]:
+        """Delete by id; returns the ids that existed.  Device: clear bits + zero rows."""
+        with self._rwlock.write_lock():
+            removed: list[Any] = []
+            rows: list[int] = []
+            for _id in ids:
+                row = self._id2idx.pop(_id, None)
+                if row is not None:
+                    self._docs[row] = None
+                    self._free.append(row)
+                    rows.append(row)
+                    removed.append(_id)
+            if rows:
+                self._engine.delete_rows(np.asarray(rows, dtype=np.int64))
+                self._invalidate()
+                if self._active_indices.size:
+                    gone = np.asarray(rows, dtype=np.int64)
+                    self._active_indices = self._active_indices[~np.isin(self._active_indices, gone)]
+            return removed
+
+    # ------------------------------------------------------------------ search
+    def _validate_queries(self, query_vecs) -> tuple[np.ndarray, bool]:
+        raw = np.ascontiguousarray(query_vecs, dtype=Float)
+        if raw.ndim == 1:
+            if raw.shape[0] != self.dim:
+                raise ValueError(f"query vector dim mismatch: expected {self.dim}, got {raw.shape[0]}")
+            return raw[None, :], True
+        if raw.ndim == 2:
+            if raw.shape[1] != self.dim:
+                raise ValueError(
+                    f"query vectors dim mismatch: expected last dim {self.dim}, got {raw.shape[1]}"
+                )
+            return raw, False
+        raise ValueError(
+            f"query expects 1D or 2D array with last dim {self.dim}; got shape {tuple(raw.shape)}"
+        )
+
+    def _candidate_mask(self, where: Optional[WhereT], ids: Optional[list[Any]]) -> Optional[np.ndarray]:
+        """Row mask for ``ids`` / ``where`` (None = every active row).  Same selection rules as the
+        reference's candidate builder (pico_vdb.py:604-658): ``ids`` -> mapped rows; a one-key dict is
+        equality or ``{"$in": [...]}`` over the candidate docs; anything else is called as a
+        predicate over the active docs and intersected."""
+        if ids is None and where is None:
+            return None
+        n = len(self._ids)
+        mask = np.zeros(n, dtype=bool)
+        docs = self._docs
+        if ids is not None:
+            for s in ids:
+                row = self._id2idx.get(s)
+                if row is not None:
+                    mask[row] = True
+            base_rows = np.flatnonzero(mask)
+        else:
+            base_rows = self._active_indices
+        if where is None:
+            return mask
+        if isinstance(where, dict) and len(where) == 1:
+            ((key, val),) = where.items()
+            if isinstance(val, dict) and set(val.keys()) == {"$in"}:
+                wanted = set(val["$in"])
+                keep = [i for i in base_rows if docs[i] is not None and docs[i].get(key) in wanted]
+            else:
+                keep = [i for i in base_rows if docs[i] is not None and docs[i].get(key) == val]
+            out = np.zeros(n, dtype=bool)
+            if keep:
+                out[np.asarray(keep, dtype=np.int64)] = True
+            return out
+        passed = np.zeros(n, dtype=bool)
+        for i in self._active_indices:
+            d = docs[i]
+            if d is not None and where(d):  # type: ignore[operator]
+                passed[i] = True
+        return passed if ids is None else (mask & passed)
+
+    def search(
+        self,
+        query_vecs: np.ndarray,
+        top_k: int = 10,
+        prefilter: Optional[np.ndarray] = None,
+        precision: Optional[str] = None,
+    ) -> tuple[np.ndarray, np.ndarray]:
+        """Array-level search: (Q, dim) or (dim,) queries -> (scores (Q, k) f32, rows (Q, k) int64).
+
+        This is the entry point the throughput metric times: no dict assembly, no Python loops.
+        ``prefilter`` is an optional bool mask over row slots.  Rows index ``_ids`` / ``_docs``.
+        """
+        raw, _ = self._validate_queries(query_vecs)
+        with self._rwlock.read_lock():
+            return self._engine.search(raw, int(top_k), prefilter, precision=precision or self._precision)
+
+    @_timed("query")
+    def query(
+        self,
+        query_vecs: np.ndarray,
+        top_k: int = 10,
+        better_than: Optional[float] = None,
+        where: Optional[WhereT] = None,
+        ids: Optional[list[Any]] = None,
+        ef_search: Optional[int] = None,
+        hnsw_ef_search: Optional[int] = None,
+    ) -> Union[list[list[dict[str, Any]]], list[dict[str, Any]]]:
+        """Exact cosine top-k.  Same results contract as the reference's NumPy path."""
+        raw, is_single = self._validate_queries(query_vecs)
+        num_q = raw.shape[0]
+        with self._rwlock.read_lock():
+            if not self._id2idx:
+                return [[] for _ in range(num_q)]  # also for a single query (reference quirk Q2)
+            mask = self._candidate_mask(where, ids)
+            n_cand = len(self._id2idx) if mask is None else int(np.count_nonzero(mask))
+            if n_cand == 0:
+                return [[] for _ in range(num_q)]
+            filtered = ids is not None or where is not None
+            base = top_k + self._adaptive_buffer if filtered else top_k
+            k_eff = min(base, n_cand)
+            self._last_k_eff = int(k_eff)
+            # which numpy strategy the reference would have used; the device does one fused select
+            self._last_topk_strategy = (
+                "argsort" if (k_eff / n_cand) > self._argsort_threshold else "argpartition"
+            )
+            if k_eff < 1:
+                return [[] for _ in range(num_q)]
+            scores, rows = self._engine.search(raw, int(k_eff), mask, precision=self._precision)
+            docs = self._docs
+            n_slots = len(self._ids)
+            recheck = callable(where)
+            out: list[list[dict[str, Any]]] = []
+            for qi in range(num_q):
+                hits: list[dict[str, Any]] = []
+                for row, score in zip(rows[qi].tolist(), scores[qi].tolist()):
+                    if row < 0 or row >= n_slots:
+                        continue
+                    doc = docs[row]
+                    if doc is None:
+                        continue
+                    if better_than is not None and score < better_than:
+                        continue
+                    if recheck and not where(doc):  # type: ignore[operator]
+                        continue
+                    hits.append({**doc, K_METRICS: float(score)})
+                    if len(hits) == top_k:
+                        break
+                out.append(hits)
+        return out[0] if is_single else out
+
+    def query_one(
+        self,
+        query_vec: np.ndarray,
+        top_k: int = 10,
+        better_than: Optional[float] = None,
+        where: Optional[Callable[[dict[str, Any]], bool]] = None,
+        ids: Optional[list[Any]] = None,
+        ef_search: Optional[int] = None,
+        hnsw_ef_search: Optional[int] = None,
+    ) -> list[dict[str, Any]]:
+        return self.query(  # type: ignore[return-value]
+            query_vec, top_k=top_k, better_than=better_than, where=where, ids=ids,
+            ef_search=ef_search, hnsw_ef_search=hnsw_ef_search,
+        )
+
+    # ------------------------------------------------------------------ maintenance
+    def stats(self) -> dict[str, Any]:
+        with self._rwlock.read_lock():
+            active = len(self._id2idx)
+            total = len(self._ids)
+            sizes = {}
+            for fn in (_ids_path, _meta_path, _vecs_path):
+                p = fn(self._path)
+                try:
+                    if os.path.exists(p):
+                        sizes[os.path.basename(p)] = os.path.getsize(p)
+                except OSError:
+                    pass
+            return {
+                "active": active,
+                "deleted": total - active,
+                "total": total,
+                "dim": self.dim,
+                "faiss": False,
+                "memmap": self._use_memmap,
+                "file_sizes": sizes,
+                "device": self._device,
+                "precision": self._precision,
+            }
+
+    def vacuum(self) -> None:
+        """Drop deleted slots: device-side row compaction + remapped host lists."""
+        with self._rwlock.write_lock():
+            if not self._free:
+                return
+            keep = sorted(self._id2idx.values())
+            self._engine.compact(np.asarray(keep, dtype=np.int64))
+            self._invalidate()
+            self._ids = [self._ids[i] for i in keep]
+            self._docs = [self._docs[i] for i in keep]
+            self._id2idx = {_id: i for i, _id in enumerate(self._ids)}
+            self._active_indices = np.arange(len(self._ids), dtype=np.int64)
+            self._free = []
+
+    def rebuild_index(self) -> None:
+        """There is no ANN index to rebuild on the exact path; kept for API compatibility."""
+        with self._rwlock.write_lock():
+            return None
+
+    # ------------------------------------------------------------------ getters
+    def _record(self, row: int, _id: Any, include_vector: bool) -> dict[str, Any]:
+        rec = dict(self._docs[row] or {K_ID: _id})
+        if include_vector:
+            rec[K_VECTOR] = self._engine.fetch_rows(np.asarray([row], dtype=np.int64))[0].copy()
+        return rec
+
+    def get(self, ids: Union[Any, list[Any]], include_vector: bool = False):
+        with self._rwlock.read_lock():
+            if isinstance(ids, str):
+                row = self._id2idx.get(ids)
+                return None if row is None else self._record(row, ids, include_vector)
+            found = [(i, self._id2idx.get(i)) for i in ids]
+            found = [(i, r) for i, r in found if r is not None]
+            recs = [dict(self._docs[r] or {K_ID: i}) for i, r in found]
+            if include_vector and found:
+                vecs = self._engine.fetch_rows(np.asarray([r for _, r in found], dtype=np.int64))
+                for rec, v in zip(recs, vecs):
+                    rec[K_VECTOR] = v.copy()
+            return recs
+
+    def get_by_id(self, sid: Any, include_vector: bool = False) -> Optional[dict[str, Any]]:
+        warnings.warn(
+            "get_by_id() is deprecated: use get(id) or get([ids])", DeprecationWarning, stacklevel=2
+        )
+        return self.get(sid, include_vector=include_vector)  # type: ignore[return-value]
+
+    def get_all(self, include_vector: bool = False, include_deleted: bool = False) -> list[dict[str, Any]]:
+        with self._rwlock.read_lock():
+            vecs = self._vectors if include_vector else None
+            out: list[dict[str, Any]] = []
+            if include_deleted:
+                for row, (_id, doc) in enumerate(zip(self._ids, self._docs)):
+                    if doc is None:
+                        out.append({K_ID: _id})
+                        continue
+                    rec = dict(doc)
+                    rec[K_ID] = _id
+                    if vecs is not None:
+                        rec[K_VECTOR] = vecs[row].copy()
+                    out.append(rec)
+                return out
+            for row in self._active_indices.tolist():
+                _id, doc = self._ids[row], self._docs[row]
+                if _id is None or doc is None:
+                    continue
+                rec = dict(doc)
+                rec[K_ID] = _id
+                if vecs is not None:
+                    rec[K_VECTOR] = vecs[row].copy()
+                out.append(rec)
+            return out
+
+    def close(self) -> None:
+        """Release the device store (also happens on garbage collection)."""
+        eng = getattr(self, "_engine", None)
+        if eng is not None and hasattr(eng, "close"):
+            eng.close()

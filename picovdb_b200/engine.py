@@ -1,0 +1,231 @@
+"""``DeviceStore``: numpy-facing wrapper of one ``pvdb_store_t`` handle.
+
+This is the device-resident half of the reference's store (``_vectors`` + ``_active_indices``,
+picovdb/pico_vdb.py:136,143) and the array-level search entry point the metric times:
+normalised-or-raw queries in, ``(scores, rows)`` out.  All arithmetic happens in the CUDA
+library; this file only marshals pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+
+def _f32c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i64c(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pack_row_mask(mask: np.ndarray) -> np.ndarray:
+    """bool (n,) -> uint32 words, bit (r & 31) of word (r >> 5) (the C-ABI bitmap layout)."""
+    mask = np.asarray(mask, dtype=bool)
+    n = mask.shape[0]
+    nwords = (n + 31) // 32
+    packed = np.packbits(mask, bitorder="little")
+    buf = np.zeros(nwords * 4, dtype=np.uint8)
+    buf[: packed.shape[0]] = packed
+    return buf.view("<u4")
+
+
+def unpack_row_mask(words: np.ndarray, n: int) -> np.ndarray:
+    bits = np.unpackbits(np.ascontiguousarray(words, dtype="<u4").view(np.uint8), bitorder="little")
+    return bits[:n].astype(bool)
+
+
+class DeviceStore:
+    """Owns one native store on one GPU."""
+
+    def __init__(
+        self,
+        dim: int,
+        device: int = 0,
+        reserve_rows: int = 0,
+        keep_f32: bool = True,
+        bf16_mirror: bool = False,
+        fixed_capacity: bool = False,
+    ) -> None:
+        self._lib = N.load()
+        flags = (N.STORE_F32 if keep_f32 else 0) | (N.STORE_BF16 if bf16_mirror else 0)
+        if fixed_capacity:
+            flags |= N.STORE_FIXED_CAPACITY
+        h = C.c_void_p()
+        N.check(self._lib.pvdb_store_create(C.byref(h), int(device), int(dim), int(reserve_rows), flags))
+        self._h = h
+        self.dim = int(dim)
+        self.device = int(device)
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value:
+            self._lib.pvdb_store_destroy(h)
+
+    def __del__(self) -> None:  # pragma: no cover - interpreter shutdown ordering
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if self._h is None:
+            raise RuntimeError("DeviceStore is closed")
+        return self._h
+
+    def info(self) -> N.StoreInfo:
+        out = N.StoreInfo()
+        N.check(self._lib.pvdb_store_info(self.handle, C.byref(out)))
+        return out
+
+    @property
+    def rows(self) -> int:
+        return int(self.info().rows)
+
+    def reserve(self, rows: int) -> None:
+        N.check(self._lib.pvdb_store_reserve(self.handle, int(rows)))
+
+    def set_row_base(self, base: int) -> None:
+        N.check(self._lib.pvdb_store_set_row_base(self.handle, int(base)))
+
+    # -- writes ------------------------------------------------------------------------------
+    def upsert_rows(self, vecs: np.ndarray, rows: np.ndarray) -> None:
+        """rows[i] := normalise(vecs[i]); rows must be unique within one call."""
+        vecs = _f32c(vecs)
+        rows = _i64c(rows)
+        if vecs.ndim != 2 or vecs.shape[1] != self.dim or rows.shape != (vecs.shape[0],):
+            raise ValueError(f"upsert_rows expects (n, {self.dim}) vectors and (n,) rows")
+        N.check(self._lib.pvdb_store_upsert(self.handle, _ptr(vecs), _ptr(rows), vecs.shape[0]))
+
+    def upsert_range(self, vecs: np.ndarray, row0: int) -> None:
+        vecs = _f32c(vecs)
+        if vecs.ndim != 2 or vecs.shape[1] != self.dim:
+            raise ValueError(f"upsert_range expects (n, {self.dim}) vectors")
+        N.check(self._lib.pvdb_store_upsert_range(self.handle, _ptr(vecs), int(row0), vecs.shape[0]))
+
+    def upsert_range_dev(self, dev_ptr: int, row0: int, n: int, stream: int = 0) -> None:
+        """Device-resident source (n x dim fp32 at ``dev_ptr``), enqueued on ``stream``."""
+        N.check(
+            self._lib.pvdb_store_upsert_range_dev(
+                self.handle, C.c_void_p(dev_ptr), int(row0), int(n), C.c_void_p(stream or None)
+            )
+        )
+
+    def upsert_rows_dev(self, dev_vecs: int, dev_rows: int, n: int, max_row: int, stream: int = 0) -> None:
+        N.check(
+            self._lib.pvdb_store_upsert_dev(
+                self.handle, C.c_void_p(dev_vecs), C.c_void_p(dev_rows), int(n), int(max_row),
+                C.c_void_p(stream or None),
+            )
+        )
+
+    def delete_rows(self, rows) -> None:
+        rows = _i64c(rows)
+        N.check(self._lib.pvdb_store_delete(self.handle, _ptr(rows), rows.shape[0]))
+
+    def upload(self, vecs: np.ndarray, row0: int = 0, active: Optional[np.ndarray] = None) -> None:
+        """Raw load of already-normalised rows; ``active`` is a bool mask over those rows."""
+        vecs = _f32c(vecs)
+        if vecs.ndim != 2 or vecs.shape[1] != self.dim:
+            raise ValueError(f"upload expects (n, {self.dim}) vectors")
+        bits = None if active is None else pack_row_mask(active)
+        N.check(self._lib.pvdb_store_upload(self.handle, int(row0), vecs.shape[0], _ptr(vecs), _ptr(bits)))
+
+    def compact(self, keep_rows) -> None:
+        keep = _i64c(keep_rows)
+        N.check(self._lib.pvdb_store_compact(self.handle, _ptr(keep), keep.shape[0]))
+
+    # -- reads -------------------------------------------------------------------------------
+    def fetch_rows(self, rows) -> np.ndarray:
+        rows = _i64c(rows)
+        out = np.empty((rows.shape[0], self.dim), dtype=np.float32)
+        N.check(self._lib.pvdb_store_fetch(self.handle, _ptr(rows), rows.shape[0], _ptr(out)))
+        return out
+
+    def download(self, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.rows - row0
+        out = np.empty((n, self.dim), dtype=np.float32)
+        N.check(self._lib.pvdb_store_download(self.handle, int(row0), int(n), _ptr(out)))
+        return out
+
+    def active_mask(self) -> np.ndarray:
+        n = self.rows
+        words = np.zeros((n + 31) // 32, dtype="<u4")
+        N.check(self._lib.pvdb_store_active_bits(self.handle, _ptr(words)))
+        return unpack_row_mask(words, n)
+
+    def search(
+        self,
+        queries: np.ndarray,
+        k: int,
+        prefilter: Optional[np.ndarray] = None,
+        precision: str = "auto",
+        normalized: bool = False,
+        rescore: bool = True,
+    ) -> tuple[np.ndarray, np.ndarray]:
+        """(Q, dim) fp32 queries -> (scores (Q, k) f32 descending, rows (Q, k) int64).
+
+        ``prefilter`` is a bool row mask or already-packed uint32 words; rows must have both
+        their active bit and their prefilter bit set to be scored.  Short results are padded with
+        -inf / -1.
+        """
+        q = _f32c(queries)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"search expects (Q, {self.dim}) queries")
+        nq = q.shape[0]
+        k = int(k)
+        if k < 1:
+            raise ValueError("k must be >= 1")
+        bits = None
+        if prefilter is not None:
+            pf = np.asarray(prefilter)
+            bits = pack_row_mask(pf) if pf.dtype == np.bool_ else np.ascontiguousarray(pf, dtype="<u4")
+        flags = N.PRECISIONS[precision]
+        if normalized:
+            flags |= N.SEARCH_QUERIES_NORMALIZED
+        if not rescore:
+            flags |= N.SEARCH_NO_RESCORE
+        scores = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        N.check(self._lib.pvdb_search(self.handle, _ptr(q), nq, k, _ptr(bits), flags, _ptr(scores), _ptr(rows)))
+        return scores, rows
+
+    def search_dev(self, d_queries: int, nq: int, k: int, d_scores: int, d_rows: int, d_prefilter: int = 0,
+                   precision: str = "auto", normalized: bool = False, rescore: bool = True, stream: int = 0) -> None:
+        """Device pointers in / out; only enqueues work on ``stream`` (a ``cudaStream_t`` as int;
+        0 = CUDA's legacy default stream, which is also torch's default stream)."""
+        flags = N.PRECISIONS[precision]
+        if normalized:
+            flags |= N.SEARCH_QUERIES_NORMALIZED
+        if not rescore:
+            flags |= N.SEARCH_NO_RESCORE
+        N.check(
+            self._lib.pvdb_search_dev(
+                self.handle, C.c_void_p(d_queries), int(nq), int(k), C.c_void_p(d_prefilter or None), flags,
+                C.c_void_p(d_scores), C.c_void_p(d_rows), C.c_void_p(stream or None),
+            )
+        )
+
+
+def merge_topk_dev(device: int, d_scores: int, d_rows: int, nlists: int, nq: int, k: int, d_out_scores: int,
+                   d_out_rows: int, stream: int = 0, scores_stride: int = 0, rows_stride: int = 0) -> None:
+    """Merge ``nlists`` per-shard (nq, k) results; strides are in elements (0 = contiguous)."""
+    lib = N.load()
+    N.check(
+        lib.pvdb_merge_topk_dev(
+            int(device), C.c_void_p(d_scores), C.c_void_p(d_rows), int(nlists), int(nq), int(k),
+            int(scores_stride), int(rows_stride),
+            C.c_void_p(d_out_scores), C.c_void_p(d_out_rows), C.c_void_p(stream or None),
+        )
+    )

@@ -1,0 +1,144 @@
+"""Row-sharded search across the GPUs of one box: one process per GPU, ``torch.distributed``.
+
+SURVEY.md 8(e): the database rows are split into contiguous, equal blocks (global row r lives on
+rank ``r // rows_per_rank``); every rank holds the full query batch, scans its own shard with the
+same kernels as the single-GPU path and produces a local (Q, k) list whose row indices are already
+global (``row_base``); ONE all-gather of the packed {rows, scores} blocks (Q*k*12 bytes per rank)
+feeds the k-way merge kernel, after which every rank holds the same final (Q, k).  The reference
+has no counterpart (it is single process); the merged result equals what one store holding all
+rows would return.
+
+torch is used here for what it is good at: process-group plumbing, device buffers, streams.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total_rows: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of rows owned by ``rank``: [row0, row1).  Blocks are ceil(total/world)
+    rows, rounded up to a multiple of 32 so every shard's bitmap starts on a word boundary."""
+    per = -(-total_rows // world_size)
+    per = (per + 31) // 32 * 32
+    row0 = min(total_rows, rank * per)
+    return row0, min(total_rows, row0 + per)
+
+
+def owner_of(row: int, total_rows: int, world_size: int) -> int:
+    per = -(-total_rows // world_size)
+    per = (per + 31) // 32 * 32
+    return min(world_size - 1, row // per)
+
+
+def packed_result_bytes(nq: int, k: int) -> int:
+    """Bytes of one rank's packed result block: nq*k int64 rows, then nq*k fp32 scores, padded to
+    16 bytes so consecutive blocks keep both arrays aligned."""
+    return (nq * k * 12 + 15) // 16 * 16
+
+
+class ShardedSearch:
+    """Search over a row-sharded store.  Every rank constructs one around its local shard.
+
+    ``local``   engine with ``search`` / ``search_dev`` / ``set_row_base`` (a ``DeviceStore``)
+    ``row0``    global index of the shard's first row
+    ``merge``   test hook only: a host merge function for process groups without a GPU (gloo);
+                with CUDA tensors the merge always runs in the library's kernel.
+    """
+
+    def __init__(self, local, row0: int, group=None, merge: Optional[Callable] = None) -> None:
+        self.local = local
+        self.row0 = int(row0)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._host_merge = merge
+        local.set_row_base(self.row0)
+        self._bufs: dict[tuple[int, int], dict[str, torch.Tensor]] = {}
+
+    # ------------------------------------------------------------------ device path
+    def _buffers(self, nq: int, k: int, device) -> dict[str, torch.Tensor]:
+        key = (nq, k)
+        b = self._bufs.get(key)
+        if b is None:
+            nbytes = packed_result_bytes(nq, k)
+            b = {
+                "local": torch.empty(nbytes, dtype=torch.uint8, device=device),
+                "all": torch.empty(self.world * nbytes, dtype=torch.uint8, device=device),
+                "scores": torch.empty((nq, k), dtype=torch.float32, device=device),
+                "rows": torch.empty((nq, k), dtype=torch.int64, device=device),
+            }
+            self._bufs[key] = b
+        return b
+
+    def search_dev(self, d_queries: torch.Tensor, k: int, precision: str = "auto", normalized: bool = False,
+                   d_prefilter: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """CUDA tensors in (``(Q, dim)`` fp32), CUDA tensors out; enqueued on torch's current stream.
+        The returned tensors are reused by the next call with the same (Q, k)."""
+        from .engine import merge_topk_dev
+
+        nq = d_queries.shape[0]
+        b = self._buffers(nq, k, d_queries.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        n_out = nq * k
+        loc = b["local"]
+        # packed block: rows (int64) first, then scores (fp32)
+        self.local.search_dev(
+            d_queries.data_ptr(), nq, k, loc.data_ptr() + n_out * 8, loc.data_ptr(),
+            d_prefilter=d_prefilter.data_ptr() if d_prefilter is not None else 0,
+            precision=precision, normalized=normalized, stream=stream,
+        )
+        if self.world == 1:
+            gathered = loc
+        else:
+            dist.all_gather_into_tensor(b["all"], loc, group=self.group)
+            gathered = b["all"]
+        block = packed_result_bytes(nq, k)
+        merge_topk_dev(
+            d_queries.device.index or 0, gathered.data_ptr() + n_out * 8, gathered.data_ptr(), self.world, nq, k,
+            b["scores"].data_ptr(), b["rows"].data_ptr(), stream=stream,
+            scores_stride=block // 4, rows_stride=block // 8,
+        )
+        return b["scores"], b["rows"]
+
+    # ------------------------------------------------------------------ host-buffer path
+    def search(self, queries: np.ndarray, k: int, prefilter: Optional[np.ndarray] = None,
+               precision: str = "auto") -> tuple[np.ndarray, np.ndarray]:
+        """numpy in / numpy out.  ``prefilter`` is this rank's slice of the row mask."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if self._host_merge is None and torch.cuda.is_available():
+            dq = torch.from_numpy(q).cuda(non_blocking=True)
+            dp = None
+            if prefilter is not None:
+                from .engine import pack_row_mask
+
+                dp = torch.from_numpy(pack_row_mask(prefilter).view(np.int32)).cuda(non_blocking=True)
+            s, r = self.search_dev(dq, k, precision=precision, d_prefilter=dp)
+            return s.cpu().numpy(), r.cpu().numpy()
+        # process group without GPUs (tests): same packing / gather / merge flow on host tensors
+        if self._host_merge is None:
+            raise RuntimeError("ShardedSearch needs CUDA (no CPU compute path)")
+        s_loc, r_loc = self.local.search(q, k, prefilter, precision=precision)
+        r_loc = np.where(r_loc >= 0, r_loc + self._host_row_base(), r_loc)
+        nq = q.shape[0]
+        packed = np.zeros(packed_result_bytes(nq, k), dtype=np.uint8)
+        packed[: nq * k * 8] = r_loc.astype("<i8").view(np.uint8).ravel()
+        packed[nq * k * 8 : nq * k * 12] = s_loc.astype("<f4").view(np.uint8).ravel()
+        loc = torch.from_numpy(packed)
+        if self.world == 1:
+            gathered = loc
+        else:
+            gathered = torch.empty(self.world * loc.numel(), dtype=torch.uint8)
+            dist.all_gather_into_tensor(gathered, loc, group=self.group)
+        blocks = gathered.numpy().reshape(self.world, -1)
+        n_out = nq * k
+        rows = [blk[: n_out * 8].view("<i8").reshape(nq, k) for blk in blocks]
+        scores = [blk[n_out * 8 : n_out * 12].view("<f4").reshape(nq, k) for blk in blocks]
+        return self._host_merge(scores, rows, k)
+
+    def _host_row_base(self) -> int:
+        # a test engine that does not implement row_base itself gets the offset added here
+        return 0 if getattr(self.local, "applies_row_base", False) else self.row0

@@ -142,7 +142,27 @@ def case_records(tmp):
     return out
 
 
+def case_refstore():
+    """A store saved by the reference itself (3 files, with one deleted row): load-compat fixture."""
+    base = os.path.join(HERE, "refstore")
+    for suffix in (".ids.json", ".vecs.npy", ".meta.json"):
+        if os.path.exists(base + suffix):
+            os.remove(base + suffix)
+    rng = np.random.default_rng(11)
+    raw = rng.standard_normal((12, 6)).astype(np.float32)
+    db = PicoVectorDB(embedding_dim=6, storage_file=base, no_faiss=True)
+    db.upsert([{K_VECTOR: raw[i], K_ID: f"doc{i}", "text": f"t{i}", "n": i} for i in range(12)])
+    db.delete(["doc4"])
+    db.store_additional_data(owner="golden", version=3)
+    db.save()
+    q = rng.standard_normal(6).astype(np.float32)
+    res = db.query(q, top_k=4)
+    with open(base + ".expect.json", "w") as f:
+        json.dump({"raw": raw.tolist(), "query": q.tolist(), "top4": res}, f, indent=1, sort_keys=True)
+
+
 def main():
+    case_refstore()
     with tempfile.TemporaryDirectory() as tmp:
         np.savez_compressed(os.path.join(HERE, "task20.npz"), **case_task20(tmp))
         np.savez_compressed(

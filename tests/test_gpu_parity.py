@@ -1,0 +1,296 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  All tests need a B200.
+
+Tolerances (BASELINE.json north_star): fp32 paths -- scores within 1e-5 relative of the
+reference, ids identical wherever the score gap exceeds that tolerance; bf16 paths -- 1e-2.
+Index outputs of integer work (row ids, padding, active bitmap) are compared exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import picovdb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+F32_RTOL = 1e-5
+F32_ATOL = 2e-6  # scores near zero: |err| <= eps * sum|q_i v_i| <= ~1e-6 for unit vectors
+BF16_RTOL = 1e-2
+BF16_ATOL = 4e-3
+
+
+@pytest.fixture
+def store_factory():
+    from picovdb_b200.engine import DeviceStore
+
+    made = []
+
+    def make(dim, **kw):
+        s = DeviceStore(dim, **kw)
+        made.append(s)
+        return s
+
+    yield make
+    for s in made:
+        s.close()
+
+
+def _gauss(n, dim, seed):
+    return np.random.default_rng(seed).standard_normal((n, dim)).astype(np.float32)
+
+
+# ------------------------------------------------------------------ write side
+@pytest.mark.parametrize("dim", [1, 2, 3, 5, 16, 100, 384, 768, 1024, 1536])
+def test_upsert_normalises_like_reference(store_factory, dim):
+    # reference _normalize (pico_vdb.py:58-68) incl. zero -> e0; fp32 tolerance 1e-6 as in the
+    # reference's own tests (tests/test_more.py:258-260)
+    raw = _gauss(70, dim, dim) * np.float32(37.5)
+    raw[3] = 0.0
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_rows(raw, np.arange(70))
+    got = s.download()
+    want = O.normalize_rows(raw)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(got[3], want[3])
+    assert got.dtype == np.float32 and got.flags["C_CONTIGUOUS"]
+    info = s.info()
+    assert (info.rows, info.active, info.dim) == (70, 70, dim)
+    assert info.ld_f32 % 4 == 0 and info.ld_bf16 % 8 == 0
+    np.testing.assert_array_equal(s.fetch_rows([5, 3, 69]), got[[5, 3, 69]])
+
+
+def test_golden_normalize_vectors(store_factory):
+    g = np.load(os.path.join(GOLDEN, "normalize.npz"))
+    for key in [k for k in g.files if k.startswith("in_")]:
+        dim = int(key[3:]) if key != "in_34" else 2
+        s = store_factory(dim)
+        s.upsert_range(g[key], 0)
+        np.testing.assert_allclose(s.download(), g["out_" + key[3:]], rtol=1e-6, atol=1e-7)
+
+
+def test_scatter_delete_bitmap_and_growth(store_factory):
+    dim = 24
+    s = store_factory(dim)
+    raw = _gauss(5000, dim, 1)
+    rows = np.random.default_rng(2).permutation(9000)[:5000]
+    s.upsert_rows(raw, rows)  # scattered rows, forces growth, leaves holes
+    info = s.info()
+    assert info.rows == rows.max() + 1 and info.active == 5000 and info.capacity >= info.rows
+    want = np.zeros((info.rows, dim), np.float32)
+    want[rows] = O.normalize_rows(raw)
+    np.testing.assert_allclose(s.download(), want, rtol=1e-6, atol=1e-7)
+    mask = np.zeros(info.rows, bool)
+    mask[rows] = True
+    np.testing.assert_array_equal(s.active_mask(), mask)
+    dead = rows[:1234]
+    s.delete_rows(dead)
+    mask[dead] = False
+    want[dead] = 0
+    np.testing.assert_array_equal(s.active_mask(), mask)
+    np.testing.assert_array_equal(s.download()[dead], 0)
+    assert s.info().active == 5000 - 1234
+    # overwrite some rows and re-activate a deleted one
+    s.upsert_rows(raw[:10], dead[:10])
+    want[dead[:10]] = O.normalize_rows(raw[:10])
+    np.testing.assert_allclose(s.download(), want, rtol=1e-6, atol=1e-7)
+    assert s.info().active == 5000 - 1234 + 10
+
+
+def test_upload_download_compact_roundtrip(store_factory):
+    dim = 10
+    v = O.normalize_rows_fast(_gauss(333, dim, 3))
+    active = np.random.default_rng(4).random(333) > 0.3
+    v[~active] = 0
+    s = store_factory(dim, bf16_mirror=True)
+    s.upload(v, 0, active)
+    np.testing.assert_array_equal(s.download(), v)  # raw load: bit exact
+    np.testing.assert_array_equal(s.active_mask(), active)
+    keep = np.flatnonzero(active)
+    s.compact(keep)
+    assert s.info().rows == keep.size == s.info().active
+    np.testing.assert_array_equal(s.download(), v[keep])
+    qn, _ = O.prepare_queries(_gauss(2, dim, 5), dim)
+    sc, rows = s.search(qn, 5)
+    ref_s, ref_r = O.search(v[keep], qn, 5)
+    O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    # the mirror was compacted too
+    sc16, rows16 = s.search(qn, 5, precision="bf16")
+    O.compare_topk(sc16, rows16, ref_s, ref_r, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
+def test_fixed_capacity_error(store_factory):
+    from picovdb_b200 import _native as N
+
+    s = store_factory(4, reserve_rows=1024, fixed_capacity=True)
+    s.upsert_range(_gauss(1024, 4, 0), 0)
+    with pytest.raises(N.NativeError) as ei:
+        s.upsert_range(_gauss(1, 4, 0), 1024)
+    assert ei.value.code == N.PVDB_ERR_CAPACITY and "capacity exceeded" in ei.value.message
+
+
+# ------------------------------------------------------------------ single-query scan
+@pytest.mark.parametrize("dim", [3, 16, 20, 48, 100, 384, 768, 1024, 2052])
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_scan_matches_oracle(store_factory, dim, k):
+    n = 3001
+    raw = _gauss(n, dim, 100 + dim)
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(raw, 0)
+    store = s.download()
+    queries = _gauss(3, dim, 7)
+    queries[1] = 0.0  # zero query -> e0 (pico_vdb.py:585-590)
+    qn, _ = O.prepare_queries(queries, dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    sc, rows = s.search(queries, k, precision="f32")
+    st = O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    assert st["recall"] >= 0.999
+    # pre-normalised flag gives the same answer
+    sc2, rows2 = s.search(qn, k, precision="f32", normalized=True)
+    O.compare_topk(sc2, rows2, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    # bf16 mirror scan: looser tolerance, recall reported against the fp32 reference
+    sc16, rows16 = s.search(queries, k, precision="bf16")
+    fin = np.isfinite(ref_s)
+    assert np.array_equal(np.isfinite(sc16), fin)
+    if dim >= 48 and k >= 10:
+        assert O.recall_at_k(rows16, ref_r) >= 0.9
+    # each returned score must be the bf16-rounded dot product of its own row within tolerance
+    for qi in range(3):
+        exact = store[rows16[qi]] @ qn[qi]
+        np.testing.assert_allclose(sc16[qi], exact, rtol=BF16_RTOL, atol=BF16_ATOL)
+
+
+def test_scan_masks_prefilter_and_padding(store_factory):
+    dim, n, k = 64, 5000, 10
+    raw = _gauss(n, dim, 11)
+    s = store_factory(dim)
+    s.upsert_range(raw, 0)
+    dead = np.random.default_rng(1).choice(n, size=int(0.3 * n), replace=False)
+    s.delete_rows(dead)
+    store = s.download()
+    active = np.ones(n, bool)
+    active[dead] = False
+    qn, _ = O.prepare_queries(_gauss(4, dim, 12), dim)
+    cat = np.arange(n) % 10
+    for pf in (None, cat == 0, cat % 2 == 0, np.zeros(n, bool), np.arange(n) == 4321):
+        ref_s, ref_r = O.search(store, qn, k, active, pf)
+        sc, rows = s.search(qn, k, prefilter=pf, precision="f32", normalized=True)
+        O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+        live = rows[rows >= 0]
+        assert active[live].all() and (pf is None or np.asarray(pf)[live].all())
+    # fewer candidates than k: -inf / -1 padding, exact
+    few = np.zeros(n, bool)
+    few[np.flatnonzero(active)[:3]] = True
+    sc, rows = s.search(qn, k, prefilter=few, precision="f32", normalized=True)
+    assert (rows[:, 3:] == -1).all() and np.isneginf(sc[:, 3:]).all() and (rows[:, :3] >= 0).all()
+
+
+@pytest.mark.parametrize("k", [129, 300, 1000])
+def test_scan_large_k_paging(store_factory, k):
+    dim, n = 32, 1500
+    s = store_factory(dim)
+    s.upsert_range(_gauss(n, dim, 21), 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(_gauss(2, dim, 22), dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    sc, rows = s.search(qn, k, precision="f32", normalized=True)
+    O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    for qi in range(2):
+        assert len(set(rows[qi].tolist())) == k  # no row returned twice across pages
+
+
+def test_ties_resolve_to_lowest_row(store_factory):
+    dim = 8
+    v = np.zeros((200, dim), np.float32)
+    v[:, 0] = 1.0  # all rows identical -> all scores equal
+    s = store_factory(dim)
+    s.upsert_range(v, 0)
+    sc, rows = s.search(v[:1], 7)
+    assert rows[0].tolist() == list(range(7)) and np.allclose(sc, 1.0)
+
+
+def test_empty_store_and_row_base(store_factory):
+    s = store_factory(4)
+    sc, rows = s.search(np.ones((2, 4), np.float32), 3)
+    assert (rows == -1).all() and np.isneginf(sc).all()
+    s.upsert_range(np.eye(4, dtype=np.float32), 0)
+    s.set_row_base(1000)
+    sc, rows = s.search(np.eye(4, dtype=np.float32)[2:3], 2)
+    assert rows[0, 0] == 1002 and sc[0, 0] == pytest.approx(1.0)
+
+
+# ------------------------------------------------------------------ golden fixtures via the C ABI
+@pytest.mark.parametrize(
+    "name,k", [("gauss_n600_d48.npz", 10), ("gauss_n400_d384_del30.npz", 10), ("gauss_n900_d20_k100.npz", 100)]
+)
+def test_golden_fixtures_cabi(store_factory, name, k):
+    g = np.load(os.path.join(GOLDEN, name))
+    n, dim = g["raw"].shape
+    s = store_factory(dim)
+    s.upsert_range(g["raw"], 0)
+    dead = np.flatnonzero(g["deleted"])
+    if dead.size:
+        s.delete_rows(dead)
+    np.testing.assert_allclose(s.download(), g["store"], rtol=1e-6, atol=1e-7)
+    cat = np.arange(n) % 10
+    subset = np.zeros(n, bool)
+    subset[::7] = True
+    for key, pf in (("", None), ("where_eq", cat == 0), ("where_in", np.isin(cat, [1, 2, 3])),
+                    ("where_fn", cat % 2 == 0), ("subset", subset)):
+        sc, rows = s.search(g["queries"], k, prefilter=pf, precision="f32")
+        ref_r = g[f"ids_{key}" if key else "ids"]
+        ref_s = g[f"scores_{key}" if key else "scores"]
+        O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_properties_at_scale(store_factory):
+    """1M x 128 (0.5 GB): self-query returns self with score 1; results are sorted; idempotent;
+    deleting the winner promotes the runner-up; agrees with the chunked oracle."""
+    import torch
+
+    dim, n, k = 128, 1_000_000, 10
+    s = store_factory(dim, reserve_rows=n)
+    gen = torch.Generator(device="cuda").manual_seed(123)
+    chunk = 250_000
+    for r0 in range(0, n, chunk):
+        x = torch.randn(chunk, dim, device="cuda", generator=gen)
+        s.upsert_range_dev(x.data_ptr(), r0, chunk)
+    torch.cuda.synchronize()
+    probe = np.array([0, 123_456, 999_999])
+    qv = s.fetch_rows(probe)
+    sc, rows = s.search(qv, k, precision="f32")
+    assert rows[:, 0].tolist() == probe.tolist()
+    np.testing.assert_allclose(sc[:, 0], 1.0, rtol=1e-5)
+    assert np.all(np.diff(sc, axis=1) <= 0)
+    sc_b, rows_b = s.search(qv, k, precision="f32")
+    np.testing.assert_array_equal(rows, rows_b)
+    np.testing.assert_array_equal(sc, sc_b)
+    store = s.download()
+    ref_s, ref_r = O.search_chunked(store, O.prepare_queries(qv, dim)[0], k)
+    O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    s.delete_rows(probe)
+    sc2, rows2 = s.search(qv, k, precision="f32")
+    np.testing.assert_array_equal(rows2[:, : k - 1], rows[:, 1:])
+
+
+def test_merge_topk_kernel(store_factory):
+    import torch
+    from picovdb_b200.engine import merge_topk_dev
+
+    rng = np.random.default_rng(5)
+    nl, nq, k = 8, 37, 10
+    parts_s = np.sort(rng.standard_normal((nl, nq, k)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    parts_r = rng.permutation(nl * nq * k).reshape(nl, nq, k).astype(np.int64)
+    parts_s[3, :, 6:] = -np.inf  # a short shard
+    parts_r[3, :, 6:] = -1
+    ds = torch.from_numpy(parts_s).cuda()
+    dr = torch.from_numpy(parts_r).cuda()
+    out_s = torch.empty(nq, k, dtype=torch.float32, device="cuda")
+    out_r = torch.empty(nq, k, dtype=torch.int64, device="cuda")
+    merge_topk_dev(0, ds.data_ptr(), dr.data_ptr(), nl, nq, k, out_s.data_ptr(), out_r.data_ptr(),
+                   torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ref_s, ref_r = O.merge_topk(list(parts_s), list(parts_r), k)
+    np.testing.assert_array_equal(out_r.cpu().numpy(), ref_r)
+    np.testing.assert_array_equal(out_s.cpu().numpy(), ref_s)
