@@ -331,7 +331,8 @@ def run_b200(args, world, rank, local_rank):
     clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel: scan launches only (pre-normalised query)
-    qn_dev = torch.nn.functional.normalize(q_dev[:64], dim=1).contiguous()
+    n_qn = min(64, n_pool)
+    qn_dev = torch.nn.functional.normalize(q_dev[:n_qn], dim=1).contiguous()
     out_s = torch.empty(k, dtype=torch.float32, device=dev)
     out_r = torch.empty(k, dtype=torch.int64, device=dev)
     n_scan = 50
@@ -342,7 +343,7 @@ def run_b200(args, world, rank, local_rank):
     l0 = N.kernel_launches()
     ev0.record()
     for j in range(n_scan):
-        store.search_dev(qn_dev[j % 64].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32",
+        store.search_dev(qn_dev[j % n_qn].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32",
                          normalized=True, stream=stream)
     ev1.record()
     torch.cuda.synchronize()
