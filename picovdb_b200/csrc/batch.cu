@@ -1,13 +1,637 @@
+// Batched queries: S = Qn . V^T on the 5th-generation tensor cores with a fused mask + top-k
+// epilogue, then an fp32 re-scoring pass.  Replaces the batched form of
+//     scores = vecs @ V.T ; argpartition ; argsort        (picovdb/pico_vdb.py:683-714)
+// without ever writing the Q x N score matrix to HBM.
+//
+// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor loads a 128-row query tile slice (A) and a
+//               256-row database tile slice (B), 128 bytes of K each, into a 4-stage shared-memory
+//               ring (128B swizzle), completion on mbarriers.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma (kind::tf32 on the fp32 matrix or
+//               kind::f16 on the bf16 mirror), M=128 x N=256, accumulating in TMEM; tcgen05.commit
+//               releases ring slots and publishes finished accumulators.  TMEM holds two
+//               accumulators (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of i+1.
+//   warps 4-7   epilogue: thread t owns query t of the tile (TMEM lane t).  It streams the 256
+//               scores of each tile out of TMEM (tcgen05.ld 32x32b.x32), skips columns whose
+//               active/prefilter bit is clear, and appends every score above its running threshold
+//               to its candidate pool; when a pool fills, the warp sorts it co-operatively (bitonic
+//               network in registers), keeps the best k_sel and raises the threshold.
+// Work unit = (query tile, contiguous chunk of database tiles); each unit leaves a sorted list of
+// its best k_sel keys per query.  finalize_batch_kernel merges the lists of all chunks per query,
+// re-scores the survivors exactly in fp32 against the fp32 matrix (tensor-core inputs are rounded
+// to tf32 / bf16; the north star asks for 1e-5 fp32 scores) and writes the top k.
+//
+// Tensor-core roofline: algorithmic flops = 2 * Q * N * dim per batch.
+#include <cuda.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "batch.cuh"
 #include "store.cuh"
 
 namespace pvdb {
 
-bool batch_path_available() { return false; }
+// ---------------------------------------------------------------------------- tile constants
+constexpr int kBM = 128;            // queries per tile (UMMA M, TMEM lanes)
+constexpr int kBN = 256;            // database rows per tile (UMMA N, TMEM columns per accumulator)
+constexpr int kKBytes = 128;        // K bytes per pipeline stage == one 128B swizzle atom
+constexpr int kStages = 4;
+constexpr int kStageABytes = kBM * kKBytes;  // 16 KB
+constexpr int kStageBBytes = kBN * kKBytes;  // 32 KB
+constexpr int kStageBytes = kStageABytes + kStageBBytes;
+constexpr int kBatchThreads = 256;
+constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
+constexpr int kMaxSel = 224;        // largest k_sel (pool of 256 keeps a 32-column chunk of headroom)
+constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
+constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
+constexpr size_t kBatchSmem = 1024 /*align*/ + static_cast<size_t>(kStages) * kStageBytes + 256;
 
-int search_batch(pvdb_store*, bool, const float*, const __nv_bfloat16*, int64_t, int, const uint32_t*, bool, float*,
-                 int64_t*, cudaStream_t) {
-  return fail(PVDB_ERR_UNSUPPORTED, "batched tensor-core path not built");
+struct BatchParams {
+  int64_t nq;            // queries in the batch
+  int64_t n_rows;        // database rows (high-water mark)
+  int k_blocks;          // ceil(dim * elem / 128)
+  int q_tiles;           // ceil(nq / 128)
+  int n_tiles;           // ceil(n_rows / 256)
+  int n_chunks;          // chunks of database tiles
+  int k_sel;             // candidates kept per (unit, query)
+  int pool_cap;          // 64 / 128 / 256 keys per (unit, query)
+  const uint32_t* active;
+  const uint32_t* prefilter;
+  uint64_t* pools;       // [n_units][128][pool_cap]
+};
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spin on the phase parity.  A broken pipeline would otherwise hang the GPU until the watchdog;
+// after ~2^31 polls the kernel traps so the failure surfaces as a CUDA error instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows 128 B apart, 8-row groups
+// 1024 B apart (SBO), descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  const uint64_t lo = static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (1ull << 16);
+  const uint64_t hi = static_cast<uint64_t>(1024u >> 4) | (1ull << 14) | (2ull << 29);
+  return lo | (hi << 32);
+}
+// instruction descriptor: D=f32, A/B = tf32 (2) or bf16 (1), both K-major, N=256, M=128
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16) {
+  const uint32_t fmt = bf16 ? 1u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) |
+         (static_cast<uint32_t>(kBM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------- warp bitonic sort
+// 32*NI keys, element e = i*32 + lane, sorted descending.
+template <int NI>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[NI], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * NI; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int sj = stride >> 5;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          if ((i & sj) == 0) {
+            const int e = i * 32 + lane;
+            const bool desc = (e & size) == 0;
+            const uint64_t a = key[i], b = key[i | sj];
+            if ((a < b) == desc) {
+              key[i] = b;
+              key[i | sj] = a;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int e = i * 32 + lane;
+          const uint64_t other = shfl_xor_u64(key[i], stride);
+          const bool desc = (e & size) == 0;
+          const bool lower = (lane & stride) == 0;
+          const bool take_max = (desc == lower);
+          const uint64_t mx = key[i] > other ? key[i] : other;
+          const uint64_t mn = key[i] > other ? other : key[i];
+          key[i] = take_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
+// Co-operative prune of one query's pool: keep the best k_sel keys (sorted, at the front).
+// Returns (through the references) the pool's new count and threshold.
+template <int NI>
+__device__ __forceinline__ void prune_pool(uint64_t* pool, int count, int k_sel, int lane, int& new_count,
+                                           float& new_thr) {
+  uint64_t key[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int e = i * 32 + lane;
+    key[i] = (e < count) ? pool[e] : 0ull;
+  }
+  warp_sort_desc<NI>(key, lane);
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int e = i * 32 + lane;
+    if (e < k_sel) pool[e] = key[i];
+  }
+  // k-th key (entry k_sel-1) decides the new threshold
+  const int ke = k_sel - 1;
+  uint64_t kv = key[0];
+#pragma unroll
+  for (int i = 1; i < NI; ++i)
+    if ((ke >> 5) == i) kv = key[i];
+  kv = shfl_u64(kv, ke & 31);
+  new_count = count < k_sel ? count : k_sel;
+  new_thr = (count >= k_sel && kv != 0ull) ? key_score(kv) : -INFINITY;
+}
+
+// ---------------------------------------------------------------------------- the GEMM + top-k kernel
+template <bool BF16, int NI>
+__global__ void __launch_bounds__(kBatchThreads, 1)
+batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
+                  const BatchParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * kStageBytes);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_units = p.q_tiles * p.n_chunks;
+  const int tiles_per_chunk = (p.n_tiles + p.n_chunks - 1) / p.n_chunks;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      constexpr int kElemsPerStage = BF16 ? 64 : 32;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int chunk = u / p.q_tiles;
+        const int qt = u - chunk * p.q_tiles;
+        const int t0 = chunk * tiles_per_chunk;
+        const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+            const uint32_t b_dst = a_dst + kStageABytes;
+            mbar_expect_tx(full_bar(stage), kStageBytes);
+            tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
+            tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, t * kBN);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BF16);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int chunk = u / p.q_tiles;
+        const int t0 = chunk * tiles_per_chunk;
+        const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+            const uint64_t da = make_smem_desc(a_addr);
+            const uint64_t db = make_smem_desc(a_addr + kStageABytes);
+#pragma unroll
+            for (int j = 0; j < kKBytes / 32; ++j) {
+              // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
+              umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                         (kb | j) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(empty_bar(stage));  // ring slot reusable once these MMAs retire
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          tcgen05_commit(tfull_bar(acc));  // accumulator complete
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= epilogue: mask + running top-k =======================
+    const int ew = warp - 4;          // == warp % 4: the TMEM lane quarter this warp may read
+    const int ql = ew * 32 + lane;    // query (TMEM lane) owned by this thread
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int chunk = u / p.q_tiles;
+      const int qt = u - chunk * p.q_tiles;
+      const int t0 = chunk * tiles_per_chunk;
+      const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
+      uint64_t* pool = p.pools + (static_cast<size_t>(u) * kBM + ql) * p.pool_cap;
+      uint64_t* warp_pools = p.pools + (static_cast<size_t>(u) * kBM + ew * 32) * p.pool_cap;
+      const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
+      float thr = live ? -INFINITY : INFINITY;  // padding queries never collect candidates
+      int cnt = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        const int64_t row0 = static_cast<int64_t>(t) * kBN;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+#pragma unroll 1
+        for (int cb = 0; cb < kBN / 32; ++cb) {
+          const int64_t wi = (row0 >> 5) + cb;
+          // active words exist up to the allocated capacity and are zero past the last row; the
+          // prefilter only has ceil(rows/32) words, so it is consulted only where a row is active
+          uint32_t mw = __ldg(p.active + wi);
+          if (mw != 0u && p.prefilter) mw &= __ldg(p.prefilter + wi);
+          if (mw == 0u) continue;  // warp-uniform: every lane sees the same columns
+          uint32_t v[32];
+          tmem_ld_32x32(taddr0 + static_cast<uint32_t>(cb * 32), v);
+          const uint32_t rbase = static_cast<uint32_t>(row0) + static_cast<uint32_t>(cb * 32);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = __uint_as_float(v[j]);
+            if (((mw >> j) & 1u) && sc > thr) {
+              pool[cnt] = make_key(sc, rbase + j);
+              ++cnt;
+            }
+          }
+          // pools that could overflow during the next 32 columns are pruned now (warp co-operative)
+          unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 32);
+          if (need) __syncwarp();
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int c = __shfl_sync(0xffffffffu, cnt, src);
+            int nc;
+            float nt;
+            prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
+            if (lane == src) {
+              cnt = nc;
+              thr = nt;
+            }
+            __syncwarp();
+          }
+        }
+        // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+      // unit finished: leave a sorted, zero-padded list of k_sel keys per query
+      __syncwarp();
+      for (int src = 0; src < 32; ++src) {
+        const int c = __shfl_sync(0xffffffffu, cnt, src);
+        int nc;
+        float nt;
+        prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
+        (void)nc;
+        (void)nt;
+      }
+      __syncwarp();
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------- finalize
+// One block per query: merge the per-chunk lists (block bitonic sort in shared memory, in rounds
+// when the lists do not fit at once), re-score the best k_sel rows exactly in fp32 and emit top k.
+constexpr int kFinalThreads = 256;
+constexpr int kFinalCap = 4096;  // keys sorted per round (32 KB of shared memory)
+
+__device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < (n_pow2 >> 1); i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint64_t a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFinalThreads)
+finalize_batch_kernel(const uint64_t* __restrict__ pools, int pool_cap, int k_sel, int q_tiles, int n_chunks,
+                      int64_t nq, int k, const float* __restrict__ qn, int ldq, const float* __restrict__ f32,
+                      int ld32, int rescore, int64_t row_base, float* __restrict__ out_scores,
+                      int64_t* __restrict__ out_rows) {
+  __shared__ uint64_t keys[kFinalCap];
+  const int64_t q = blockIdx.x;
+  const int qt = static_cast<int>(q / kBM);
+  const int ql = static_cast<int>(q % kBM);
+  const int lists_per_round = (kFinalCap - k_sel) / k_sel;  // >= 1 since k_sel <= 224
+  int kept = 0;  // keys[0..kept) = best so far (sorted)
+  for (int c0 = 0; c0 < n_chunks; c0 += lists_per_round) {
+    const int c1 = min(n_chunks, c0 + lists_per_round);
+    const int fresh = (c1 - c0) * k_sel;
+    for (int i = threadIdx.x; i < fresh; i += blockDim.x) {
+      const int c = c0 + i / k_sel, j = i % k_sel;
+      const size_t u = static_cast<size_t>(c) * q_tiles + qt;
+      keys[kept + i] = pools[(u * kBM + ql) * pool_cap + j];
+    }
+    const int filled = kept + fresh;
+    int n_pow2 = 2;
+    while (n_pow2 < filled) n_pow2 <<= 1;
+    for (int i = filled + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
+    block_sort_desc(keys, n_pow2);
+    kept = min(filled, k_sel);
+  }
+  // keys[0..kept) sorted descending by tensor-core score
+  if (rescore) {
+    // exact fp32 dot product of the query with each surviving row (one warp per candidate)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* q4 = reinterpret_cast<const float4*>(qn + q * ldq);
+    __syncthreads();
+    for (int c = warp; c < kept; c += kFinalThreads / 32) {
+      const uint64_t key = keys[c];
+      if (key == 0ull) continue;
+      const uint32_t row = key_row(key);
+      const float4* v4 = reinterpret_cast<const float4*>(f32 + static_cast<size_t>(row) * ld32);
+      float acc = 0.f;
+      for (int i = lane; i < (ld32 >> 2); i += 32) {
+        const float4 a = __ldg(v4 + i);
+        const float4 b = q4[i];
+        acc = fmaf(a.x, b.x, acc);
+        acc = fmaf(a.y, b.y, acc);
+        acc = fmaf(a.z, b.z, acc);
+        acc = fmaf(a.w, b.w, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) keys[c] = make_key(acc, row);
+    }
+    __syncthreads();
+    int n_pow2 = 2;
+    while (n_pow2 < kept) n_pow2 <<= 1;
+    for (int i = kept + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
+    block_sort_desc(keys, n_pow2);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const uint64_t key = (j < kept) ? keys[j] : 0ull;
+    out_scores[q * k + j] = key ? key_score(key) : -INFINITY;
+    out_rows[q * k + j] = key ? row_base + static_cast<int64_t>(key_row(key)) : -1ll;
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+bool batch_path_available() { return get_encode_fn() != nullptr; }
+
+// 2-D row-major matrix [rows][inner] with `ld` elements between rows; box = 128 bytes x box_rows
+static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, int64_t rows, int ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(PVDB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * (bf16 ? 2u : 4u)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(bf16 ? 64 : 32), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PVDB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+  return PVDB_OK;
+}
+
+// number of database-tile chunks: enough units to fill every SM several times, with a last wave
+// that is as full as possible (units are statically strided over a grid of 148 CTAs)
+static int choose_chunks(int q_tiles, int n_tiles) {
+  const int max_chunks = n_tiles;
+  int want = (kNumSMs * 4 + q_tiles - 1) / q_tiles;         // ~4 waves
+  want = std::max(1, std::min(want, std::max(1, n_tiles / 2)));  // but at least 2 tiles per unit
+  want = std::min(want, max_chunks);
+  int best = want;
+  double best_waste = 1e30;
+  for (int nc = want; nc <= std::min(max_chunks, want + 40); ++nc) {
+    const int tiles_per_chunk = (n_tiles + nc - 1) / nc;
+    const int used_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    if (used_chunks != nc) continue;  // keep chunk ranges non-empty
+    const int64_t units = static_cast<int64_t>(q_tiles) * nc;
+    const int64_t waves = (units + kNumSMs - 1) / kNumSMs;
+    const double waste = static_cast<double>(waves * kNumSMs) / units;
+    if (waste < best_waste - 1e-9) {
+      best_waste = waste;
+      best = nc;
+    }
+  }
+  // `best` may still leave empty trailing chunks; normalise
+  const int tpc = (n_tiles + best - 1) / best;
+  return (n_tiles + tpc - 1) / tpc;
+}
+
+template <bool BF16>
+static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p, int grid,
+                          cudaStream_t st) {
+  auto run = [&](auto kern) -> int {
+    PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmem)));
+    kern<<<grid, kBatchThreads, kBatchSmem, st>>>(mq, mdb, p);
+    PVDB_LAUNCH_CHECK();
+    return PVDB_OK;
+  };
+  switch (p.pool_cap) {
+    case 64: return run(batch_topk_kernel<BF16, 2>);
+    case 128: return run(batch_topk_kernel<BF16, 4>);
+    default: return run(batch_topk_kernel<BF16, 8>);
+  }
+}
+
+int batch_max_k(bool use_bf16, bool rescore) { return kMaxSel - (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0); }
+
+int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq, int k,
+                 const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+  const bool rescore = !no_rescore && s->f32.ptr != nullptr;
+  const int k_sel = k + (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0);
+  if (k_sel > kMaxSel) return fail(PVDB_ERR_UNSUPPORTED, "batch: k=%d too large for the fused tensor-core path", k);
+  BatchParams p{};
+  p.nq = nq;
+  p.n_rows = s->rows;
+  p.k_blocks = use_bf16 ? (s->dim + 63) / 64 : (s->dim + 31) / 32;
+  p.q_tiles = static_cast<int>((nq + kBM - 1) / kBM);
+  p.n_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
+  p.n_chunks = choose_chunks(p.q_tiles, p.n_tiles);
+  p.k_sel = k_sel;
+  p.pool_cap = k_sel <= 32 ? 64 : (k_sel <= 96 ? 128 : 256);
+  p.active = static_cast<const uint32_t*>(s->active.ptr);
+  p.prefilter = d_pref;
+  const int64_t n_units = static_cast<int64_t>(p.q_tiles) * p.n_chunks;
+  const size_t pool_bytes = static_cast<size_t>(n_units) * kBM * p.pool_cap * sizeof(uint64_t);
+  PVDB_TRY(s->d_misc.ensure(pool_bytes));
+  p.pools = static_cast<uint64_t*>(s->d_misc.ptr);
+
+  CUtensorMap mq, mdb;
+  if (use_bf16) {
+    PVDB_TRY(encode_map(&mq, true, d_qn16, s->dim, nq, s->ldq, kBM));
+    PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
+  } else {
+    PVDB_TRY(encode_map(&mq, false, d_qn, s->dim, nq, s->ldq, kBM));
+    PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
+  }
+  const int grid = static_cast<int>(std::min<int64_t>(n_units, kNumSMs));
+  if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
+  else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
+
+  finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
+      p.pools, p.pool_cap, p.k_sel, p.q_tiles, p.n_chunks, nq, k, d_qn, s->ldq, static_cast<const float*>(s->f32.ptr),
+      s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores, d_out_rows);
+  PVDB_LAUNCH_CHECK();
+  return PVDB_OK;
 }
 
 }  // namespace pvdb

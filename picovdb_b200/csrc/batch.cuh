@@ -8,9 +8,11 @@ struct pvdb_store;
 
 namespace pvdb {
 
-constexpr int64_t kBatchMinQueries = 3;  // fewer queries are cheaper as back-to-back HBM scans
+constexpr int64_t kBatchMinQueries = 5;  // fewer queries are cheaper as back-to-back HBM scans
 
 bool batch_path_available();
+// largest k the fused tensor-core path selects in one pass (larger k uses the paged scan path)
+int batch_max_k(bool use_bf16, bool rescore);
 
 // d_qn: nq x ldq normalised fp32 queries; d_qn16: the same in bf16 (only for use_bf16).
 int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq, int k,

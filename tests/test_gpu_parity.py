@@ -294,3 +294,127 @@ def test_merge_topk_kernel(store_factory):
     ref_s, ref_r = O.merge_topk(list(parts_s), list(parts_r), k)
     np.testing.assert_array_equal(out_r.cpu().numpy(), ref_r)
     np.testing.assert_array_equal(out_s.cpu().numpy(), ref_s)
+
+
+# ------------------------------------------------------------------ batched tensor-core path
+def _check_batch(sc, rows, store, qn, k, active, pf, ref_r, score_rtol, score_atol, min_recall):
+    """Returned scores must be the dot product of their own row (within tolerance), lists sorted,
+    rows unique / active / inside the prefilter, and recall against the fp32 reference high."""
+    nq = qn.shape[0]
+    assert sc.shape == (nq, k) and rows.shape == (nq, k)
+    for qi in range(nq):
+        live = rows[qi] >= 0
+        n_live = int(live.sum())
+        assert n_live == int((ref_r[qi] >= 0).sum()), f"query {qi}: result count differs"
+        assert live[:n_live].all() and np.isneginf(sc[qi, n_live:]).all()
+        r = rows[qi, :n_live]
+        assert len(set(r.tolist())) == n_live
+        if active is not None:
+            assert active[r].all()
+        if pf is not None:
+            assert np.asarray(pf)[r].all()
+        exact = store[r] @ qn[qi]
+        np.testing.assert_allclose(sc[qi, :n_live], exact, rtol=score_rtol, atol=score_atol)
+        assert np.all(np.diff(sc[qi, :n_live]) <= 0)
+    rec = O.recall_at_k(rows, ref_r)
+    assert rec >= min_recall, f"recall {rec}"
+    return rec
+
+
+@pytest.mark.parametrize("dim", [16, 100, 384, 768, 1024])
+@pytest.mark.parametrize("nq,k", [(5, 10), (64, 1), (130, 10), (300, 100)])
+def test_batch_tf32_rescored_matches_oracle(store_factory, dim, nq, k):
+    n = 5003  # not a multiple of the 256-row tile
+    s = store_factory(dim)
+    s.upsert_range(_gauss(n, dim, 200 + dim), 0)
+    store = s.download()
+    queries = _gauss(nq, dim, 31)
+    queries[2] = 0.0
+    qn, _ = O.prepare_queries(queries, dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    sc, rows = s.search(queries, k, precision="tf32")
+    _check_batch(sc, rows, store, qn, k, None, None, ref_r, F32_RTOL, F32_ATOL, 0.995)
+    # auto precision picks the same path for a batch this large
+    sc2, rows2 = s.search(queries, k)
+    np.testing.assert_array_equal(rows2, rows)
+    np.testing.assert_array_equal(sc2, sc)
+
+
+def test_batch_masks_and_prefilter(store_factory):
+    dim, n, k, nq = 64, 7001, 10, 40
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 41), 0)
+    dead = np.random.default_rng(1).choice(n, size=int(0.3 * n), replace=False)
+    s.delete_rows(dead)
+    store = s.download()
+    active = np.ones(n, bool)
+    active[dead] = False
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 42), dim)
+    cat = np.arange(n) % 10
+    few = np.zeros(n, bool)
+    few[np.flatnonzero(active)[:4]] = True
+    for pf in (None, cat == 0, cat % 2 == 0, np.zeros(n, bool), few):
+        ref_s, ref_r = O.search(store, qn, k, active, pf)
+        for prec, rtol, atol, rec in (("tf32", F32_RTOL, F32_ATOL, 0.995), ("bf16", F32_RTOL, F32_ATOL, 0.98)):
+            sc, rows = s.search(qn, k, prefilter=pf, precision=prec, normalized=True)
+            _check_batch(sc, rows, store, qn, k, active, pf, ref_r, rtol, atol, rec)
+
+
+def test_batch_without_rescoring_reports_tensor_core_scores(store_factory):
+    dim, n, k, nq = 384, 4000, 10, 33
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 51), 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 52), dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    sc, rows = s.search(qn, k, precision="tf32", normalized=True, rescore=False)
+    _check_batch(sc, rows, store, qn, k, None, None, ref_r, 2e-3, 2e-3, 0.9)   # tf32 inputs: ~5e-4 relative
+    sc, rows = s.search(qn, k, precision="bf16", normalized=True, rescore=False)
+    _check_batch(sc, rows, store, qn, k, None, None, ref_r, BF16_RTOL, BF16_ATOL, 0.9)
+
+
+def test_batch_bf16_only_store(store_factory):
+    dim, n, k, nq = 384, 3000, 10, 20
+    s = store_factory(dim, keep_f32=False, bf16_mirror=True)
+    raw = _gauss(n, dim, 61)
+    s.upsert_range(raw, 0)
+    ref_store = O.normalize_rows(raw)
+    np.testing.assert_allclose(s.download(), ref_store, rtol=8e-3, atol=1e-3)  # bf16 storage
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 62), dim)
+    ref_s, ref_r = O.search(ref_store, qn, k)
+    sc, rows = s.search(qn, k, normalized=True)
+    _check_batch(sc, rows, ref_store, qn, k, None, None, ref_r, BF16_RTOL, BF16_ATOL, 0.9)
+    sc1, rows1 = s.search(qn[:1], k, normalized=True)  # single query -> bf16 scan
+    _check_batch(sc1, rows1, ref_store, qn[:1], k, None, None, ref_r[:1], BF16_RTOL, BF16_ATOL, 0.9)
+
+
+def test_batch_large_matches_chunked_oracle(store_factory):
+    """C1-like shape scaled to what the oracle finishes in seconds: 100k x 256, 1000 queries."""
+    dim, n, k, nq = 256, 100_000, 10, 1000
+    s = store_factory(dim)
+    s.upsert_range(_gauss(n, dim, 71), 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 72), dim)
+    ref_s, ref_r = O.search_chunked(store, qn, k)
+    sc, rows = s.search(qn, k, normalized=True)
+    rec = _check_batch(sc, rows, store, qn, k, None, None, ref_r, F32_RTOL, F32_ATOL, 0.999)
+    # where the reference ids agree exactly the scores must agree at 1e-5 as well
+    same = rows == ref_r
+    np.testing.assert_allclose(sc[same], ref_s[same], rtol=F32_RTOL, atol=F32_ATOL)
+    assert same.mean() >= 0.999, (rec, same.mean())
+
+
+def test_batch_through_picovectordb(tmp_path):
+    from picovdb_b200 import PicoVectorDB, K_ID
+
+    dim, n = 32, 2000
+    db = PicoVectorDB(embedding_dim=dim, storage_file=str(tmp_path / "b"))
+    v = _gauss(n, dim, 81)
+    db.upsert_array(v)
+    qs = _gauss(50, dim, 82)
+    res = db.query(qs, top_k=5)
+    qn, _ = O.prepare_queries(qs, dim)
+    ref_s, ref_r = O.search(db._vectors, qn, 5)
+    got = np.array([[r[K_ID] for r in rows] for rows in res])
+    assert (got == ref_r).mean() >= 0.995
+    db.close()
