@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Device-resident measurements of the other BASELINE.json configs (C1, C3, C4, C5) on ONE GPU.
+
+bench.py measures the headline (C2).  This tool times the kernels behind the remaining configs with
+CUDA events (inputs resident in HBM, >= 3 warm-ups, inputs larger than L2 or an L2 flush between
+iterations), checks each against the exact fp32 scan path (itself pinned to the oracle by
+tests/test_gpu_parity.py) on a few queries, and prints one JSON line per measurement.
+
+    python tools/bench_configs.py [c1 c3 c4 c5s c5b ...] [--scale 1.0]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from picovdb_b200 import _native as N  # noqa: E402
+from picovdb_b200.engine import DeviceStore, pack_row_mask  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def fill(store: DeviceStore, rows: int, dim: int, seed: int, dev) -> None:
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    chunk = max(1, min(rows, (256 << 20) // (dim * 4)))
+    stream = torch.cuda.current_stream().cuda_stream
+    for r0 in range(0, rows, chunk):
+        m = min(chunk, rows - r0)
+        x = torch.randn(m, dim, device=dev, generator=gen)
+        store.upsert_range_dev(x.data_ptr(), r0, m, stream=stream)
+        torch.cuda.synchronize()
+
+
+def flush_l2(buf):
+    buf.zero_()
+
+
+def time_search(store, q_dev, k, precision, d_pref=0, iters=10, warm=3, flush=None, normalized=False):
+    nq = q_dev.shape[0]
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=q_dev.device)
+    out_r = torch.empty((nq, k), dtype=torch.int64, device=q_dev.device)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        store.search_dev(q_dev.data_ptr(), nq, k, out_s.data_ptr(), out_r.data_ptr(), d_prefilter=d_pref,
+                         precision=precision, normalized=normalized, stream=stream)
+
+    for _ in range(warm):
+        run()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush_l2(flush)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return float(np.median(times)), out_s, out_r
+
+
+def recall_vs_exact(store, q_dev, k, out_r, d_pref=0, n_check=8):
+    """recall@k of a batch result against the exact fp32 scan on the first n_check queries."""
+    n_check = min(n_check, q_dev.shape[0])
+    ex_s = torch.empty((n_check, k), dtype=torch.float32, device=q_dev.device)
+    ex_r = torch.empty((n_check, k), dtype=torch.int64, device=q_dev.device)
+    store.search_dev(q_dev.data_ptr(), n_check, k, ex_s.data_ptr(), ex_r.data_ptr(), d_prefilter=d_pref,
+                     precision="f32", stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    a, b = out_r[:n_check].cpu().numpy(), ex_r.cpu().numpy()
+    hits = sum(len(set(x[x >= 0].tolist()) & set(y[y >= 0].tolist())) for x, y in zip(a, b))
+    total = int((b >= 0).sum())
+    return hits / max(total, 1)
+
+
+def emit(**kw):
+    print(json.dumps(kw), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5s", "c5b"])
+    ap.add_argument("--scale", type=float, default=1.0, help="scale the row counts (debugging)")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    hbm, bf16_tf, src = peaks()
+    tf32_tf = bf16_tf / 2  # nominal ratio; no tf32 GEMM peak is measured by the driver
+    l2buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    qgen = torch.Generator(device=dev).manual_seed(99)
+
+    if "c1" in args.which:
+        rows, dim, nq, k = int(100_000 * args.scale), 1024, 1000, 10
+        st = DeviceStore(dim, device=0, reserve_rows=rows)
+        fill(st, rows, dim, 123, dev)
+        q = torch.randn(nq, dim, device=dev, generator=qgen)
+        for prec in ("tf32", "f32"):
+            ms, _, out_r = time_search(st, q, k, prec, iters=5 if prec == "f32" else 20, flush=l2buf)
+            flops = 2.0 * nq * rows * dim
+            emit(config="C1 100k x 1024 fp32, 1000-query batch, top-10", path=prec, ms=ms, qps=nq / ms * 1e3,
+                 tflops=flops / ms / 1e9, frac_tf32_peak=flops / ms / 1e9 / tf32_tf, peak_tf32_assumed=tf32_tf,
+                 recall_vs_exact=recall_vs_exact(st, q, k, out_r), l2="flushed between iterations")
+        st.close()
+
+    if "c3" in args.which:
+        rows, dim, nq, k = int(10_000_000 * args.scale), 768, 4096, 100
+        st = DeviceStore(dim, device=0, reserve_rows=rows)
+        fill(st, rows, dim, 123, dev)
+        q = torch.randn(nq, dim, device=dev, generator=qgen)
+        ms, _, out_r = time_search(st, q, k, "tf32", iters=5)
+        flops = 2.0 * nq * rows * dim
+        emit(config="C3 10M x 768 fp32/tf32, 4096-query batch, top-100 (1 GPU)", path="tf32+rescore", ms=ms,
+             qps=nq / ms * 1e3, tflops=flops / ms / 1e9, frac_tf32_peak=flops / ms / 1e9 / tf32_tf,
+             peak_tf32_assumed=tf32_tf, recall_vs_exact=recall_vs_exact(st, q, k, out_r, n_check=4),
+             l2="input 30.7 GB > L2")
+        for nq2 in (16, 128, 512):
+            ms2, _, _ = time_search(st, q[:nq2].contiguous(), 10, "tf32", iters=5)
+            emit(config=f"C3-shape 10M x 768, {nq2}-query batch, top-10", path="tf32+rescore", ms=ms2,
+                 qps=nq2 / ms2 * 1e3, tflops=2.0 * nq2 * rows * dim / ms2 / 1e9,
+                 hbm_gbs=rows * dim * 4 / ms2 / 1e6, frac_hbm=rows * dim * 4 / ms2 / 1e6 / hbm)
+        st.close()
+
+    if "c4" in args.which:
+        rows, dim, k = int(5_000_000 * args.scale), 384, 10
+        st = DeviceStore(dim, device=0, reserve_rows=rows)
+        fill(st, rows, dim, 123, dev)
+        dead = np.random.default_rng(1).choice(rows, size=int(0.3 * rows), replace=False)
+        st.delete_rows(dead)
+        active = np.ones(rows, bool)
+        active[dead] = False
+        cat = np.arange(rows) % 10
+        q1 = torch.randn(1, dim, device=dev, generator=qgen)
+        for name, pf in (("mask only (30% deleted)", None), ("prefilter category even (50%)", cat % 2 == 0),
+                         ("prefilter category 0 (10%)", cat == 0)):
+            d_pref = 0
+            cand = active if pf is None else (active & pf)
+            if pf is not None:
+                words = torch.from_numpy(pack_row_mask(pf).view(np.int32)).to(dev)
+                d_pref = words.data_ptr()
+            ms, _, _ = time_search(st, q1, k, "f32", d_pref=d_pref, iters=30, flush=None)
+            algo = float(cand.sum()) * dim * 4 + rows / 8 * (2 if pf is not None else 1)
+            emit(config="C4 5M x 384 fp32, 30% deleted, single query top-10", case=name, ms=ms, qps=1e3 / ms,
+                 candidates=int(cand.sum()), algorithmic_bytes=algo, hbm_gbs=algo / ms / 1e6,
+                 frac_hbm=algo / ms / 1e6 / hbm, peak=hbm, peak_source=src)
+        st.close()
+
+    if "c5s" in args.which or "c5b" in args.which:
+        rows, dim, k = int(12_500_000 * args.scale), 384, 10  # one GPU's shard of 100M rows at N=8
+        st = DeviceStore(dim, device=0, reserve_rows=rows, keep_f32=False, bf16_mirror=True)
+        fill(st, rows, dim, 123, dev)
+        if "c5s" in args.which:
+            q1 = torch.randn(1, dim, device=dev, generator=qgen)
+            ms, _, _ = time_search(st, q1, k, "bf16", iters=30)
+            algo = rows * dim * 2 + rows / 8
+            emit(config="C5 shard 12.5M x 384 bf16 (1/8 of 100M), single query top-10", ms=ms, qps=1e3 / ms,
+                 algorithmic_bytes=algo, hbm_gbs=algo / ms / 1e6, frac_hbm=algo / ms / 1e6 / hbm, peak=hbm,
+                 peak_source=src)
+        if "c5b" in args.which:
+            nq = 4096
+            q = torch.randn(nq, dim, device=dev, generator=qgen)
+            ms, _, out_r = time_search(st, q, k, "bf16", iters=5)
+            flops = 2.0 * nq * rows * dim
+            emit(config="C5 shard 12.5M x 384 bf16 (1/8 of 100M), 4096-query batch top-10", ms=ms,
+                 qps=nq / ms * 1e3, tflops=flops / ms / 1e9, frac_bf16_peak=flops / ms / 1e9 / bf16_tf,
+                 peak=bf16_tf, peak_source=src)
+        st.close()
+    emit(kernel_launches=N.kernel_launches())
+
+
+if __name__ == "__main__":
+    main()
