@@ -12,14 +12,23 @@
 //               releases ring slots and publishes finished accumulators.  TMEM holds two
 //               accumulators (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of i+1.
 //   warps 4-7   epilogue: thread t owns query t of the tile (TMEM lane t).  It streams the 256
-//               scores of each tile out of TMEM (tcgen05.ld 32x32b.x32), skips columns whose
-//               active/prefilter bit is clear, and appends every score above its running threshold
-//               to its candidate pool; when a pool fills, the warp sorts it co-operatively (bitonic
-//               network in registers), keeps the best k_sel and raises the threshold.
-// Work unit = (query tile, contiguous chunk of database tiles); each unit leaves a sorted list of
-// its best k_sel keys per query.  finalize_batch_kernel merges the lists of all chunks per query,
-// re-scores the survivors exactly in fp32 against the fp32 matrix (tensor-core inputs are rounded
-// to tf32 / bf16; the north star asks for 1e-5 fp32 scores) and writes the top k.
+//               scores of each tile out of TMEM (tcgen05.ld 32x32b.x32, next chunk in flight while
+//               the current one is examined), turns masked columns into -inf, and compares the
+//               MAXIMUM of each 8-column group with its running threshold; only groups that beat it
+//               are examined column by column and appended to the query's candidate pool.  When a
+//               pool fills, the warp sorts it co-operatively (bitonic network in registers), keeps
+//               the best k_sel and raises the threshold.
+//
+// Schedule: a "visit" is (database tile t, query tile qt); visits are numbered tile-major
+// (v = t * q_tiles + qt) and CTA b takes v = b, b + grid, b + 2*grid, ...  At any moment the 148
+// CTAs therefore work on the same handful of database tiles, each of which is fetched from HBM
+// once and then served to the other query tiles from L2 (the first version walked one query tile
+// down a long chunk of database tiles per CTA; CTAs drifted apart and the 10M x 768 case re-read
+// the database 24x from HBM).  A CTA keeps one running (threshold, count, pool) per query tile it
+// meets; at the end it leaves a sorted list of k_sel keys per (CTA, query tile, query).
+// finalize_batch_kernel merges those lists per query, re-scores the survivors exactly in fp32
+// against the fp32 matrix (tensor-core inputs are rounded to tf32 / bf16; the north star asks for
+// 1e-5 fp32 scores) and writes the top k.
 //
 // Tensor-core roofline: algorithmic flops = 2 * Q * N * dim per batch.
 #include <cuda.h>
@@ -42,23 +51,27 @@ constexpr int kStageBBytes = kBN * kKBytes;  // 32 KB
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kBatchThreads = 256;
 constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
-constexpr int kMaxSel = 224;        // largest k_sel (pool of 256 keeps a 32-column chunk of headroom)
+constexpr int kMaxSel = 192;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom)
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
-constexpr size_t kBatchSmem = 1024 /*align*/ + static_cast<size_t>(kStages) * kStageBytes + 256;
+constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
+// shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
+constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
+constexpr size_t kStateBytes = static_cast<size_t>(kMaxQTiles) * kBM * (sizeof(float) + sizeof(uint16_t)) + kMaxQTiles;
+constexpr size_t kBatchSmem = 1024 /*align*/ + kRingBytes + 256 + kStateBytes;
 
 struct BatchParams {
-  int64_t nq;            // queries in the batch
+  int64_t nq;            // queries in this launch (<= 4096)
   int64_t n_rows;        // database rows (high-water mark)
   int k_blocks;          // ceil(dim * elem / 128)
   int q_tiles;           // ceil(nq / 128)
   int n_tiles;           // ceil(n_rows / 256)
-  int n_chunks;          // chunks of database tiles
-  int k_sel;             // candidates kept per (unit, query)
-  int pool_cap;          // 64 / 128 / 256 keys per (unit, query)
+  int k_sel;             // candidates kept per (CTA, query)
+  int pool_cap;          // 64 / 128 / 256 keys per (CTA, query tile, query)
   const uint32_t* active;
   const uint32_t* prefilter;
-  uint64_t* pools;       // [n_units][128][pool_cap]
+  uint64_t* pools;       // [grid][q_tiles][128][pool_cap]
+  uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
 };
 
 // ---------------------------------------------------------------------------- PTX wrappers
@@ -75,7 +88,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Spin on the phase parity.  A broken pipeline would otherwise hang the GPU until the watchdog;
-// after ~2^31 polls the kernel traps so the failure surfaces as a CUDA error instead.
+// after ~2^28 polls the kernel traps so the failure surfaces as a CUDA error instead.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
@@ -123,7 +136,8 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t 
         : "memory");
   }
 }
-// 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter
+// 32 lanes x 32 consecutive fp32 columns of this warp's TMEM lane quarter (asynchronous: the
+// registers are valid after tmem_ld_wait)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -135,7 +149,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Wait for outstanding tcgen05.ld.  The registers are passed as in/out operands so the compiler
+// cannot move any use of them above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                 "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 
 // shared-memory matrix descriptor: K-major tile, 128-byte swizzle, rows 128 B apart, 8-row groups
@@ -191,8 +215,8 @@ __device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[NI], int lane) {
   }
 }
 
-// Co-operative prune of one query's pool: keep the best k_sel keys (sorted, at the front).
-// Returns (through the references) the pool's new count and threshold.
+// Co-operative prune of one query's pool: keep the best k_sel keys (sorted, zero padded, at the
+// front).  Returns (through the references) the pool's new count and threshold.
 template <int NI>
 __device__ __forceinline__ void prune_pool(uint64_t* pool, int count, int k_sel, int lane, int& new_count,
                                            float& new_thr) {
@@ -219,6 +243,41 @@ __device__ __forceinline__ void prune_pool(uint64_t* pool, int count, int k_sel,
   new_thr = (count >= k_sel && kv != 0ull) ? key_score(kv) : -INFINITY;
 }
 
+// One 32-column chunk of scores for this thread's query: masked columns become -inf, then only
+// 8-column groups whose maximum beats the threshold are examined column by column.
+__device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float thr, uint64_t* pool, int& cnt,
+                                           uint32_t row_base) {
+  if (mw != 0xffffffffu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (!((mw >> j) & 1u)) v[j] = 0xff800000u;  // -inf
+  }
+  float g[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float m = __uint_as_float(v[q * 8]);
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[q * 8 + j]));
+    g[q] = m;
+  }
+  const float m_all = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  if (m_all > thr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (g[q] > thr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sc = __uint_as_float(v[q * 8 + j]);
+          if (sc > thr) {
+            pool[cnt] = make_key(sc, row_base + q * 8 + j);
+            ++cnt;
+          }
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- the GEMM + top-k kernel
 template <bool BF16, int NI>
 __global__ void __launch_bounds__(kBatchThreads, 1)
@@ -228,9 +287,12 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   // 1024-byte alignment is required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(kStages) * kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* s_thr = reinterpret_cast<float*>(smem + kRingBytes + 256);                   // [q_tiles][128]
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_thr + kMaxQTiles * kBM);            // [q_tiles][128]
+  uint8_t* s_touched = reinterpret_cast<uint8_t*>(s_cnt + kMaxQTiles * kBM);          // [q_tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -251,6 +313,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (threadIdx.x < kMaxQTiles) s_touched[threadIdx.x] = 0;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(kTmemCols)
@@ -262,8 +325,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_units = p.q_tiles * p.n_chunks;
-  const int tiles_per_chunk = (p.n_tiles + p.n_chunks - 1) / p.n_chunks;
+  const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * p.q_tiles;
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -273,23 +335,19 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int chunk = u / p.q_tiles;
-        const int qt = u - chunk * p.q_tiles;
-        const int t0 = chunk * tiles_per_chunk;
-        const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
-            const uint32_t b_dst = a_dst + kStageABytes;
-            mbar_expect_tx(full_bar(stage), kStageBytes);
-            tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
-            tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, t * kBN);
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+      for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+        const int t = static_cast<int>(v / p.q_tiles);
+        const int qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+          const uint32_t b_dst = a_dst + kStageABytes;
+          mbar_expect_tx(full_bar(stage), kStageBytes);
+          tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
+          tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, t * kBN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
@@ -302,37 +360,32 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int chunk = u / p.q_tiles;
-        const int t0 = chunk * tiles_per_chunk;
-        const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
-        for (int t = t0; t < t1; ++t) {
-          mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+      for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(full_bar(stage), phase);
-            tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
-            const uint64_t da = make_smem_desc(a_addr);
-            const uint64_t db = make_smem_desc(a_addr + kStageABytes);
+          const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+          const uint64_t da = make_smem_desc(a_addr);
+          const uint64_t db = make_smem_desc(a_addr + kStageABytes);
 #pragma unroll
-            for (int j = 0; j < kKBytes / 32; ++j) {
-              // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
-              umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
-                         (kb | j) != 0 ? 1u : 0u);
-            }
-            tcgen05_commit(empty_bar(stage));  // ring slot reusable once these MMAs retire
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
-            }
+          for (int j = 0; j < kKBytes / 32; ++j) {
+            // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                       (kb | j) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(tfull_bar(acc));  // accumulator complete
-          if (++acc == 2) {
-            acc = 0;
-            acc_phase ^= 1u;
+          tcgen05_commit(empty_bar(stage));  // ring slot reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
+        }
+        tcgen05_commit(tfull_bar(acc));  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
         }
       }
     }
@@ -340,69 +393,81 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     // ======================= epilogue: mask + running top-k =======================
     const int ew = warp - 4;          // == warp % 4: the TMEM lane quarter this warp may read
     const int ql = ew * 32 + lane;    // query (TMEM lane) owned by this thread
+    for (int qt = 0; qt < p.q_tiles; ++qt) {
+      const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
+      s_thr[qt * kBM + ql] = live ? -INFINITY : INFINITY;  // padding queries never collect candidates
+      s_cnt[qt * kBM + ql] = 0;
+    }
+    uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int chunk = u / p.q_tiles;
-      const int qt = u - chunk * p.q_tiles;
-      const int t0 = chunk * tiles_per_chunk;
-      const int t1 = min(p.n_tiles, t0 + tiles_per_chunk);
-      uint64_t* pool = p.pools + (static_cast<size_t>(u) * kBM + ql) * p.pool_cap;
-      uint64_t* warp_pools = p.pools + (static_cast<size_t>(u) * kBM + ew * 32) * p.pool_cap;
-      const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
-      float thr = live ? -INFINITY : INFINITY;  // padding queries never collect candidates
-      int cnt = 0;
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tcgen05_fence_after();
-        const int64_t row0 = static_cast<int64_t>(t) * kBN;
-        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+    for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+      const int t = static_cast<int>(v / p.q_tiles);
+      const int qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
+      uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
+      uint64_t* pool = warp_pools + static_cast<size_t>(lane) * p.pool_cap;
+      float thr = s_thr[qt * kBM + ql];
+      int cnt = s_cnt[qt * kBM + ql];
+      if (lane == 0 && ew == 0) s_touched[qt] = 1;
+      const int64_t row0 = static_cast<int64_t>(t) * kBN;
+      const uint32_t* aw = p.active + (row0 >> 5);
+      const uint32_t* pw = p.prefilter ? p.prefilter + (row0 >> 5) : nullptr;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr0, va);
 #pragma unroll 1
-        for (int cb = 0; cb < kBN / 32; ++cb) {
-          const int64_t wi = (row0 >> 5) + cb;
-          // active words exist up to the allocated capacity and are zero past the last row; the
-          // prefilter only has ceil(rows/32) words, so it is consulted only where a row is active
-          uint32_t mw = __ldg(p.active + wi);
-          if (mw != 0u && p.prefilter) mw &= __ldg(p.prefilter + wi);
-          if (mw == 0u) continue;  // warp-uniform: every lane sees the same columns
-          uint32_t v[32];
-          tmem_ld_32x32(taddr0 + static_cast<uint32_t>(cb * 32), v);
-          const uint32_t rbase = static_cast<uint32_t>(row0) + static_cast<uint32_t>(cb * 32);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = __uint_as_float(v[j]);
-            if (((mw >> j) & 1u) && sc > thr) {
-              pool[cnt] = make_key(sc, rbase + j);
-              ++cnt;
-            }
-          }
-          // pools that could overflow during the next 32 columns are pruned now (warp co-operative)
-          unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 32);
-          if (need) __syncwarp();
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const int c = __shfl_sync(0xffffffffu, cnt, src);
-            int nc;
-            float nt;
-            prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
-            if (lane == src) {
-              cnt = nc;
-              thr = nt;
-            }
-            __syncwarp();
-          }
+      for (int cb = 0; cb < kBN / 32; cb += 2) {
+        // Mask words of the two 32-column chunks of this step (warp-uniform).  Active words exist up
+        // to the allocated capacity and are zero past the last row; the prefilter only has
+        // ceil(rows/32) words, so it is consulted only where a row is active.
+        uint32_t mw0 = __ldg(aw + cb), mw1 = __ldg(aw + cb + 1);
+        if (pw != nullptr) {
+          if (mw0 != 0u) mw0 &= __ldg(pw + cb);
+          if (mw1 != 0u) mw1 &= __ldg(pw + cb + 1);
         }
-        // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
+        // chunk cb is in flight into `va`; start chunk cb+1 into `vb` before examining `va`
+        tmem_ld_wait(va);
+        tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 1) * 32), vb);
+        if (mw0 != 0u) scan_chunk(va, mw0, thr, pool, cnt, static_cast<uint32_t>(row0) + cb * 32);
+        tmem_ld_wait(vb);
+        if (cb + 2 < kBN / 32) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 2) * 32), va);
+        if (mw1 != 0u) scan_chunk(vb, mw1, thr, pool, cnt, static_cast<uint32_t>(row0) + (cb + 1) * 32);
+        // pools that could overflow during the next 64 columns are pruned now (warp co-operative)
+        unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 64);
+        if (need) __syncwarp();
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int c = __shfl_sync(0xffffffffu, cnt, src);
+          int nc;
+          float nt;
+          prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
+          if (lane == src) {
+            cnt = nc;
+            thr = nt;
+          }
+          __syncwarp();
         }
       }
-      // unit finished: leave a sorted, zero-padded list of k_sel keys per query
+      // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+      s_thr[qt * kBM + ql] = thr;
+      s_cnt[qt * kBM + ql] = static_cast<uint16_t>(cnt);
+    }
+    // all visits done: leave a sorted, zero-padded list of k_sel keys per (query tile met, query)
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps agree on s_touched
+    for (int qt = 0; qt < p.q_tiles; ++qt) {
+      if (!s_touched[qt]) continue;
+      uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
+      const int cnt = s_cnt[qt * kBM + ql];
       __syncwarp();
       for (int src = 0; src < 32; ++src) {
         const int c = __shfl_sync(0xffffffffu, cnt, src);
@@ -412,7 +477,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         (void)nc;
         (void)nt;
       }
-      __syncwarp();
+      if (ew == 0 && lane == 0) p.touched[static_cast<size_t>(blockIdx.x) * p.q_tiles + qt] = 1;
     }
   }
 
@@ -425,7 +490,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------- finalize
-// One block per query: merge the per-chunk lists (block bitonic sort in shared memory, in rounds
+// One block per query: merge the per-CTA lists (block bitonic sort in shared memory, in rounds
 // when the lists do not fit at once), re-score the best k_sel rows exactly in fp32 and emit top k.
 constexpr int kFinalThreads = 256;
 constexpr int kFinalCap = 4096;  // keys sorted per round (32 KB of shared memory)
@@ -450,22 +515,32 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n_pow2) {
 }
 
 __global__ void __launch_bounds__(kFinalThreads)
-finalize_batch_kernel(const uint64_t* __restrict__ pools, int pool_cap, int k_sel, int q_tiles, int n_chunks,
-                      int64_t nq, int k, const float* __restrict__ qn, int ldq, const float* __restrict__ f32,
-                      int ld32, int rescore, int64_t row_base, float* __restrict__ out_scores,
-                      int64_t* __restrict__ out_rows) {
+finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restrict__ touched, int n_ctas,
+                      int pool_cap, int k_sel, int q_tiles, int64_t nq, int k, const float* __restrict__ qn, int ldq,
+                      const float* __restrict__ f32, int ld32, int rescore, int64_t row_base,
+                      float* __restrict__ out_scores, int64_t* __restrict__ out_rows) {
   __shared__ uint64_t keys[kFinalCap];
+  __shared__ int s_lists[kNumSMs];
+  __shared__ int s_nlists;
   const int64_t q = blockIdx.x;
   const int qt = static_cast<int>(q / kBM);
   const int ql = static_cast<int>(q % kBM);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int b = 0; b < n_ctas; ++b)
+      if (touched[static_cast<size_t>(b) * q_tiles + qt]) s_lists[n++] = b;
+    s_nlists = n;
+  }
+  __syncthreads();
+  const int n_lists = s_nlists;
   const int lists_per_round = (kFinalCap - k_sel) / k_sel;  // >= 1 since k_sel <= 224
   int kept = 0;  // keys[0..kept) = best so far (sorted)
-  for (int c0 = 0; c0 < n_chunks; c0 += lists_per_round) {
-    const int c1 = min(n_chunks, c0 + lists_per_round);
+  for (int c0 = 0; c0 < n_lists; c0 += lists_per_round) {
+    const int c1 = min(n_lists, c0 + lists_per_round);
     const int fresh = (c1 - c0) * k_sel;
     for (int i = threadIdx.x; i < fresh; i += blockDim.x) {
       const int c = c0 + i / k_sel, j = i % k_sel;
-      const size_t u = static_cast<size_t>(c) * q_tiles + qt;
+      const size_t u = static_cast<size_t>(s_lists[c]) * q_tiles + qt;
       keys[kept + i] = pools[(u * kBM + ql) * pool_cap + j];
     }
     const int filled = kept + fresh;
@@ -550,32 +625,6 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
   return PVDB_OK;
 }
 
-// number of database-tile chunks: enough units to fill every SM several times, with a last wave
-// that is as full as possible (units are statically strided over a grid of 148 CTAs)
-static int choose_chunks(int q_tiles, int n_tiles) {
-  const int max_chunks = n_tiles;
-  int want = (kNumSMs * 4 + q_tiles - 1) / q_tiles;         // ~4 waves
-  want = std::max(1, std::min(want, std::max(1, n_tiles / 2)));  // but at least 2 tiles per unit
-  want = std::min(want, max_chunks);
-  int best = want;
-  double best_waste = 1e30;
-  for (int nc = want; nc <= std::min(max_chunks, want + 40); ++nc) {
-    const int tiles_per_chunk = (n_tiles + nc - 1) / nc;
-    const int used_chunks = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
-    if (used_chunks != nc) continue;  // keep chunk ranges non-empty
-    const int64_t units = static_cast<int64_t>(q_tiles) * nc;
-    const int64_t waves = (units + kNumSMs - 1) / kNumSMs;
-    const double waste = static_cast<double>(waves * kNumSMs) / units;
-    if (waste < best_waste - 1e-9) {
-      best_waste = waste;
-      best = nc;
-    }
-  }
-  // `best` may still leave empty trailing chunks; normalise
-  const int tpc = (n_tiles + best - 1) / best;
-  return (n_tiles + tpc - 1) / tpc;
-}
-
 template <bool BF16>
 static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p, int grid,
                           cudaStream_t st) {
@@ -586,7 +635,6 @@ static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const B
     return PVDB_OK;
   };
   switch (p.pool_cap) {
-    case 64: return run(batch_topk_kernel<BF16, 2>);
     case 128: return run(batch_topk_kernel<BF16, 4>);
     default: return run(batch_topk_kernel<BF16, 8>);
   }
@@ -594,43 +642,52 @@ static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const B
 
 int batch_max_k(bool use_bf16, bool rescore) { return kMaxSel - (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0); }
 
-int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq, int k,
-                 const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq_total,
+                 int k, const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows,
+                 cudaStream_t st) {
   const bool rescore = !no_rescore && s->f32.ptr != nullptr;
   const int k_sel = k + (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0);
   if (k_sel > kMaxSel) return fail(PVDB_ERR_UNSUPPORTED, "batch: k=%d too large for the fused tensor-core path", k);
-  BatchParams p{};
-  p.nq = nq;
-  p.n_rows = s->rows;
-  p.k_blocks = use_bf16 ? (s->dim + 63) / 64 : (s->dim + 31) / 32;
-  p.q_tiles = static_cast<int>((nq + kBM - 1) / kBM);
-  p.n_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
-  p.n_chunks = choose_chunks(p.q_tiles, p.n_tiles);
-  p.k_sel = k_sel;
-  p.pool_cap = k_sel <= 32 ? 64 : (k_sel <= 96 ? 128 : 256);
-  p.active = static_cast<const uint32_t*>(s->active.ptr);
-  p.prefilter = d_pref;
-  const int64_t n_units = static_cast<int64_t>(p.q_tiles) * p.n_chunks;
-  const size_t pool_bytes = static_cast<size_t>(n_units) * kBM * p.pool_cap * sizeof(uint64_t);
-  PVDB_TRY(s->d_misc.ensure(pool_bytes));
-  p.pools = static_cast<uint64_t*>(s->d_misc.ptr);
 
-  CUtensorMap mq, mdb;
-  if (use_bf16) {
-    PVDB_TRY(encode_map(&mq, true, d_qn16, s->dim, nq, s->ldq, kBM));
-    PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
-  } else {
-    PVDB_TRY(encode_map(&mq, false, d_qn, s->dim, nq, s->ldq, kBM));
-    PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
+  CUtensorMap mdb;
+  if (use_bf16) PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
+  else PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
+
+  const int64_t max_q = static_cast<int64_t>(kMaxQTiles) * kBM;
+  for (int64_t q0 = 0; q0 < nq_total; q0 += max_q) {
+    const int64_t nq = std::min(max_q, nq_total - q0);
+    BatchParams p{};
+    p.nq = nq;
+    p.n_rows = s->rows;
+    p.k_blocks = use_bf16 ? (s->dim + 63) / 64 : (s->dim + 31) / 32;
+    p.q_tiles = static_cast<int>((nq + kBM - 1) / kBM);
+    p.n_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
+    p.k_sel = k_sel;
+    // the epilogue prunes when fewer than 64 free slots remain, so cap >= k_sel + 64
+    p.pool_cap = k_sel <= 64 ? 128 : 256;
+    p.active = static_cast<const uint32_t*>(s->active.ptr);
+    p.prefilter = d_pref;
+    const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * p.q_tiles;
+    const int grid = static_cast<int>(std::min<int64_t>(n_visits, kNumSMs));
+    const size_t pool_bytes = static_cast<size_t>(grid) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
+    const size_t touched_bytes = (static_cast<size_t>(grid) * p.q_tiles + 255) & ~size_t(255);
+    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes));
+    p.pools = static_cast<uint64_t*>(s->d_misc.ptr);
+    p.touched = static_cast<uint8_t*>(s->d_misc.ptr) + pool_bytes;
+    PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes, st));
+
+    CUtensorMap mq;
+    if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
+    else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
+    if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
+    else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
+
+    finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
+        p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
+        static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
+        d_out_rows + q0 * k);
+    PVDB_LAUNCH_CHECK();
   }
-  const int grid = static_cast<int>(std::min<int64_t>(n_units, kNumSMs));
-  if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
-  else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
-
-  finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
-      p.pools, p.pool_cap, p.k_sel, p.q_tiles, p.n_chunks, nq, k, d_qn, s->ldq, static_cast<const float*>(s->f32.ptr),
-      s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores, d_out_rows);
-  PVDB_LAUNCH_CHECK();
   return PVDB_OK;
 }
 
