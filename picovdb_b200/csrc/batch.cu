@@ -34,6 +34,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "batch.cuh"
@@ -51,9 +52,10 @@ constexpr int kStageBBytes = kBN * kKBytes;  // 32 KB
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kBatchThreads = 256;
 constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
-constexpr int kMaxSel = 192;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom)
+constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom + 32 slots)
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
+constexpr int kDefaultQGroup = 32;  // see decode_visit
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
@@ -72,7 +74,31 @@ struct BatchParams {
   const uint32_t* prefilter;
   uint64_t* pools;       // [grid][q_tiles][128][pool_cap]
   uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
+  uint32_t* shared_thr;  // [nq] ordered-int image of the best published k_sel-th score (zeroed)
+  int q_group;         // query tiles that share a database tile back to back (visit order)
 };
+
+// Visit order: query tiles are taken in groups of q_group; inside a group visits run tile-major
+// (database tile t, then the group's query tiles).  q_group = q_tiles is pure tile-major (every
+// database tile is fetched from HBM once, but q_tiles CTAs hit the same L2 lines at the same
+// instant); smaller groups trade HBM re-reads (q_tiles / q_group passes) for less L2 contention.
+__device__ __forceinline__ void decode_visit(const BatchParams& p, int64_t v, int& t, int& qt) {
+  const int g = p.q_group;
+  const int full_groups = p.q_tiles / g;
+  const int64_t per_group = static_cast<int64_t>(p.n_tiles) * g;
+  const int64_t full = per_group * full_groups;
+  if (v < full) {
+    const int qg = static_cast<int>(v / per_group);
+    const int64_t rem = v - qg * per_group;
+    t = static_cast<int>(rem / g);
+    qt = qg * g + static_cast<int>(rem - static_cast<int64_t>(t) * g);
+  } else {
+    const int r = p.q_tiles - full_groups * g;  // > 0 here
+    const int64_t rem = v - full;
+    t = static_cast<int>(rem / r);
+    qt = full_groups * g + static_cast<int>(rem - static_cast<int64_t>(t) * r);
+  }
+}
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -336,8 +362,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
       for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
-        const int t = static_cast<int>(v / p.q_tiles);
-        const int qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
+        int t, qt;
+        decode_visit(p, v, t, qt);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
@@ -402,13 +428,23 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
-      const int t = static_cast<int>(v / p.q_tiles);
-      const int qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
+      int t, qt;
+      decode_visit(p, v, t, qt);
       uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
       uint64_t* pool = warp_pools + static_cast<size_t>(lane) * p.pool_cap;
       float thr = s_thr[qt * kBM + ql];
       int cnt = s_cnt[qt * kBM + ql];
       if (lane == 0 && ew == 0) s_touched[qt] = 1;
+      // Shared threshold: every CTA that holds k_sel candidates for this query publishes its k_sel-th
+      // score (atomicMax below).  The global k_sel-th best is >= each of them, so anything strictly
+      // below the published maximum can be skipped by everybody; without this each of the ~37 CTAs
+      // serving a query tile warms its threshold up on its own and collects ~37x more candidates.
+      const int64_t gq = static_cast<int64_t>(qt) * kBM + ql;
+      uint32_t* gthr = p.shared_thr + (gq < p.nq ? gq : 0);
+      {
+        const uint32_t g = __ldcg(gthr);
+        if (gq < p.nq && g > 1u) thr = fmaxf(thr, ordered_to_f32(g - 1u));  // keep scores >= published
+      }
       const int64_t row0 = static_cast<int64_t>(t) * kBN;
       const uint32_t* aw = p.active + (row0 >> 5);
       const uint32_t* pw = p.prefilter ? p.prefilter + (row0 >> 5) : nullptr;
@@ -446,7 +482,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
           if (lane == src) {
             cnt = nc;
-            thr = nt;
+            if (nt > thr) thr = nt;
+            if (c >= p.k_sel) atomicMax(gthr, f32_to_ordered(nt));
           }
           __syncwarp();
         }
@@ -663,18 +700,23 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     p.q_tiles = static_cast<int>((nq + kBM - 1) / kBM);
     p.n_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
     p.k_sel = k_sel;
-    // the epilogue prunes when fewer than 64 free slots remain, so cap >= k_sel + 64
-    p.pool_cap = k_sel <= 64 ? 128 : 256;
+    // the epilogue prunes when fewer than 64 free slots remain; leave at least 32 slots between
+    // prunes (cap >= k_sel + 96)
+    p.pool_cap = k_sel <= 32 ? 128 : 256;
     p.active = static_cast<const uint32_t*>(s->active.ptr);
     p.prefilter = d_pref;
+    p.q_group = std::min(p.q_tiles, kDefaultQGroup);
+    if (const char* e = getenv("PVDB_BATCH_QGROUP")) p.q_group = std::max(1, std::min(p.q_tiles, atoi(e)));
     const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * p.q_tiles;
     const int grid = static_cast<int>(std::min<int64_t>(n_visits, kNumSMs));
     const size_t pool_bytes = static_cast<size_t>(grid) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
     const size_t touched_bytes = (static_cast<size_t>(grid) * p.q_tiles + 255) & ~size_t(255);
-    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes));
+    const size_t thr_bytes = (static_cast<size_t>(nq) * sizeof(uint32_t) + 255) & ~size_t(255);
+    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes));
     p.pools = static_cast<uint64_t*>(s->d_misc.ptr);
     p.touched = static_cast<uint8_t*>(s->d_misc.ptr) + pool_bytes;
-    PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes, st));
+    p.shared_thr = reinterpret_cast<uint32_t*>(p.touched + touched_bytes);
+    PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
 
     CUtensorMap mq;
     if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, s->dim, nq, s->ldq, kBM));

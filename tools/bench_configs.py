@@ -97,6 +97,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["c1", "c3", "c4", "c5s", "c5b"])
     ap.add_argument("--scale", type=float, default=1.0, help="scale the row counts (debugging)")
+    ap.add_argument("--custom", action="append", default=[], help="rows,dim,nq,k,precision[,mirror]")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
@@ -179,6 +180,21 @@ def main():
             emit(config="C5 shard 12.5M x 384 bf16 (1/8 of 100M), 4096-query batch top-10", ms=ms,
                  qps=nq / ms * 1e3, tflops=flops / ms / 1e9, frac_bf16_peak=flops / ms / 1e9 / bf16_tf,
                  peak=bf16_tf, peak_source=src)
+        st.close()
+    for spec in args.custom:
+        # rows,dim,nq,k,precision[,mirror]   e.g. --custom 2500000,768,4096,10,tf32
+        parts = spec.split(",")
+        rows, dim, nq, k = (int(x) for x in parts[:4])
+        prec = parts[4]
+        mirror = prec == "bf16" or (len(parts) > 5 and parts[5] == "mirror")
+        st = DeviceStore(dim, device=0, reserve_rows=rows, bf16_mirror=mirror)
+        fill(st, rows, dim, 123, dev)
+        q = torch.randn(nq, dim, device=dev, generator=qgen)
+        ms, _, out_r = time_search(st, q, k, prec, iters=5, flush=l2buf if rows * dim * 4 < (512 << 20) else None)
+        flops = 2.0 * nq * rows * dim
+        emit(config=f"custom {rows} x {dim}, {nq} queries, top-{k}, {prec}", ms=ms, qps=nq / ms * 1e3,
+             tflops=flops / ms / 1e9, hbm_gbs=rows * dim * (2 if prec == "bf16" else 4) / ms / 1e6,
+             recall_vs_exact=recall_vs_exact(st, q, k, out_r, n_check=4))
         st.close()
     emit(kernel_launches=N.kernel_launches())
 
