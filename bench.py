@@ -257,6 +257,7 @@ def run_b200(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
 
     r0, r1 = shard_range(args.rows, world, rank)
