@@ -56,6 +56,7 @@ constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
 constexpr int kDefaultQGroup = 32;  // see decode_visit
+constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
@@ -75,6 +76,8 @@ struct BatchParams {
   uint64_t* pools;       // [grid][q_tiles][128][pool_cap]
   uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
   uint32_t* shared_thr;  // [nq] ordered-int image of the best published k_sel-th score (zeroed)
+  int tile_begin;        // first database tile of this launch (n_tiles counts from here)
+  const float* init_thr; // optional [nq]: a proven lower bound of each query's k_sel-th best score
   int q_group;         // query tiles that share a database tile back to back (visit order)
 };
 
@@ -370,7 +373,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const uint32_t b_dst = a_dst + kStageABytes;
           mbar_expect_tx(full_bar(stage), kStageBytes);
           tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
-          tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, t * kBN);
+          tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -421,7 +424,13 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const int ql = ew * 32 + lane;    // query (TMEM lane) owned by this thread
     for (int qt = 0; qt < p.q_tiles; ++qt) {
       const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
-      s_thr[qt * kBM + ql] = live ? -INFINITY : INFINITY;  // padding queries never collect candidates
+      float t0 = -INFINITY;
+      if (live && p.init_thr != nullptr) {
+        // scores equal to the bound must still be admitted: start one ulp below it
+        const float b = p.init_thr[static_cast<int64_t>(qt) * kBM + ql];
+        if (b > -INFINITY) t0 = ordered_to_f32(f32_to_ordered(b) - 1u);
+      }
+      s_thr[qt * kBM + ql] = live ? t0 : INFINITY;  // padding queries never collect candidates
       s_cnt[qt * kBM + ql] = 0;
     }
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
@@ -445,7 +454,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t g = __ldcg(gthr);
         if (gq < p.nq && g > 1u) thr = fmaxf(thr, ordered_to_f32(g - 1u));  // keep scores >= published
       }
-      const int64_t row0 = static_cast<int64_t>(t) * kBN;
+      const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN;
       const uint32_t* aw = p.active + (row0 >> 5);
       const uint32_t* pw = p.prefilter ? p.prefilter + (row0 >> 5) : nullptr;
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -555,7 +564,9 @@ __global__ void __launch_bounds__(kFinalThreads)
 finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restrict__ touched, int n_ctas,
                       int pool_cap, int k_sel, int q_tiles, int64_t nq, int k, const float* __restrict__ qn, int ldq,
                       const float* __restrict__ f32, int ld32, int rescore, int64_t row_base,
-                      float* __restrict__ out_scores, int64_t* __restrict__ out_rows) {
+                      float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
+                      const uint64_t* __restrict__ carry_in, uint64_t* __restrict__ carry_out,
+                      float* __restrict__ thr_out) {
   __shared__ uint64_t keys[kFinalCap];
   __shared__ int s_lists[kNumSMs];
   __shared__ int s_nlists;
@@ -572,6 +583,12 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restr
   const int n_lists = s_nlists;
   const int lists_per_round = (kFinalCap - k_sel) / k_sel;  // >= 1 since k_sel <= 224
   int kept = 0;  // keys[0..kept) = best so far (sorted)
+  if (carry_in != nullptr) {
+    // the sample pass already produced a sorted (zero padded) list of k_sel keys for this query
+    for (int j = threadIdx.x; j < k_sel; j += blockDim.x) keys[j] = carry_in[q * k_sel + j];
+    kept = k_sel;
+    __syncthreads();
+  }
   for (int c0 = 0; c0 < n_lists; c0 += lists_per_round) {
     const int c1 = min(n_lists, c0 + lists_per_round);
     const int fresh = (c1 - c0) * k_sel;
@@ -588,6 +605,17 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restr
     kept = min(filled, k_sel);
   }
   // keys[0..kept) sorted descending by tensor-core score
+  if (carry_out != nullptr) {
+    // sample pass: hand the merged list and its k_sel-th score (a proven lower bound of the final
+    // k_sel-th best) to the main pass instead of producing results
+    __syncthreads();
+    for (int j = threadIdx.x; j < k_sel; j += blockDim.x) carry_out[q * k_sel + j] = (j < kept) ? keys[j] : 0ull;
+    if (threadIdx.x == 0) {
+      const uint64_t kth = (kept >= k_sel) ? keys[k_sel - 1] : 0ull;
+      thr_out[q] = kth ? key_score(kth) : -INFINITY;
+    }
+    return;
+  }
   if (rescore) {
     // exact fp32 dot product of the query with each surviving row (one warp per candidate)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -691,6 +719,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   else PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
 
   const int64_t max_q = static_cast<int64_t>(kMaxQTiles) * kBM;
+  const int total_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
   for (int64_t q0 = 0; q0 < nq_total; q0 += max_q) {
     const int64_t nq = std::min(max_q, nq_total - q0);
     BatchParams p{};
@@ -698,7 +727,6 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     p.n_rows = s->rows;
     p.k_blocks = use_bf16 ? (s->dim + 63) / 64 : (s->dim + 31) / 32;
     p.q_tiles = static_cast<int>((nq + kBM - 1) / kBM);
-    p.n_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
     p.k_sel = k_sel;
     // the epilogue prunes when fewer than 64 free slots remain; leave at least 32 slots between
     // prunes (cap >= k_sel + 96)
@@ -707,28 +735,57 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     p.prefilter = d_pref;
     p.q_group = std::min(p.q_tiles, kDefaultQGroup);
     if (const char* e = getenv("PVDB_BATCH_QGROUP")) p.q_group = std::max(1, std::min(p.q_tiles, atoi(e)));
-    const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * p.q_tiles;
-    const int grid = static_cast<int>(std::min<int64_t>(n_visits, kNumSMs));
-    const size_t pool_bytes = static_cast<size_t>(grid) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
-    const size_t touched_bytes = (static_cast<size_t>(grid) * p.q_tiles + 255) & ~size_t(255);
+
+    // Sample pass: the first 1/16 of the tiles is searched on its own; the k_sel-th best score it
+    // finds for a query is a proven lower bound of that query's final k_sel-th best, so the main
+    // pass starts every (CTA, query) state at that threshold instead of warming each one up from
+    // -inf (which costs ~k_sel * ln(rows/k_sel) pool insertions per state).  Both passes feed the
+    // same final merge, so the result is the exact top k either way.
+    int sample_tiles = total_tiles / kSampleFraction;
+    if (const char* e = getenv("PVDB_BATCH_SAMPLE")) sample_tiles = atoi(e) > 0 ? total_tiles / atoi(e) : 0;
+    if (static_cast<int64_t>(sample_tiles) * p.q_tiles < 4 * kNumSMs) sample_tiles = 0;  // too small to pay off
+
+    const int grid_max = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(total_tiles) * p.q_tiles, kNumSMs));
+    const size_t pool_bytes = static_cast<size_t>(grid_max) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
+    const size_t touched_bytes = (static_cast<size_t>(grid_max) * p.q_tiles + 255) & ~size_t(255);
     const size_t thr_bytes = (static_cast<size_t>(nq) * sizeof(uint32_t) + 255) & ~size_t(255);
-    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes));
-    p.pools = static_cast<uint64_t*>(s->d_misc.ptr);
-    p.touched = static_cast<uint8_t*>(s->d_misc.ptr) + pool_bytes;
+    const size_t carry_bytes = sample_tiles ? ((static_cast<size_t>(nq) * k_sel * sizeof(uint64_t) + 255) & ~size_t(255)) : 0;
+    const size_t init_bytes = sample_tiles ? thr_bytes : 0;
+    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes + carry_bytes + init_bytes));
+    unsigned char* base = static_cast<unsigned char*>(s->d_misc.ptr);
+    p.pools = reinterpret_cast<uint64_t*>(base);
+    p.touched = base + pool_bytes;
     p.shared_thr = reinterpret_cast<uint32_t*>(p.touched + touched_bytes);
-    PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
+    uint64_t* carry = reinterpret_cast<uint64_t*>(base + pool_bytes + touched_bytes + thr_bytes);
+    float* init_thr = reinterpret_cast<float*>(base + pool_bytes + touched_bytes + thr_bytes + carry_bytes);
 
     CUtensorMap mq;
     if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
     else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
-    if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
-    else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
 
-    finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
-        p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
-        static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
-        d_out_rows + q0 * k);
-    PVDB_LAUNCH_CHECK();
+    auto run_pass = [&](int tile_begin, int n_tiles, const float* thr_in, const uint64_t* carry_in, uint64_t* carry_out,
+                        float* thr_out) -> int {
+      p.tile_begin = tile_begin;
+      p.n_tiles = n_tiles;
+      p.init_thr = thr_in;
+      const int64_t n_visits = static_cast<int64_t>(n_tiles) * p.q_tiles;
+      const int grid = static_cast<int>(std::min<int64_t>(n_visits, kNumSMs));
+      PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
+      if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
+      else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
+      finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
+          p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
+          static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
+          d_out_rows + q0 * k, carry_in, carry_out, thr_out);
+      PVDB_LAUNCH_CHECK();
+      return PVDB_OK;
+    };
+    if (sample_tiles > 0) {
+      PVDB_TRY(run_pass(0, sample_tiles, nullptr, nullptr, carry, init_thr));
+      PVDB_TRY(run_pass(sample_tiles, total_tiles - sample_tiles, init_thr, carry, nullptr, nullptr));
+    } else {
+      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr));
+    }
   }
   return PVDB_OK;
 }
