@@ -29,8 +29,10 @@ static int fill_empty(float* d_scores, int64_t* d_rows, int64_t n, cudaStream_t 
 // Per-query scan passes (exact fp32 accumulation, fp32 matrix or bf16 mirror).  k > kFusedK is
 // served by paging: pass p only admits keys strictly below the last key of pass p-1, which the
 // kernel keeps on the device, so no host round trip separates the passes.
-static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, int64_t nq, int k, const uint32_t* d_pref,
-                       float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+// d_qn: normalised queries (nq x ldq) or NULL, in which case d_raw (nq x dim, raw) is normalised by
+// the scan kernel itself.
+static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float* d_raw, int64_t nq, int k,
+                       const uint32_t* d_pref, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
   const int grid = scan_grid_blocks();
   const size_t list_bytes = static_cast<size_t>(grid) * kFusedK * sizeof(uint64_t);
   PVDB_TRY(s->d_partial.ensure(list_bytes + 64));
@@ -51,7 +53,9 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, int64_t nq, 
   p.next_upper = reinterpret_cast<uint64_t*>(ctrl + 8);
   p.row_base = s->row_base;
   for (int64_t q = 0; q < nq; ++q) {
-    p.query = d_qn + q * s->ldq;
+    p.query = d_qn ? d_qn + q * s->ldq : nullptr;
+    p.raw_query = d_qn ? nullptr : d_raw + q * s->dim;
+    p.dim = s->dim;
     for (int k0 = 0; k0 < k; k0 += kFusedK) {
       p.k = std::min(kFusedK, k - k0);
       p.upper = (k0 == 0) ? nullptr : p.next_upper;
@@ -92,6 +96,8 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
   __nv_bfloat16* d_qn16 = nullptr;
   if (normalised && s->ldq == s->dim && !need16) {
     d_qn = d_queries;  // already in the padded layout the kernels read: no preparation launch at all
+  } else if (!batch && !normalised) {
+    d_qn = nullptr;    // the scan kernel normalises the raw query itself (fused, no extra launch)
   } else {
     PVDB_TRY(s->d_qn.ensure(static_cast<size_t>(nq) * s->ldq * sizeof(float)));
     if (need16) {
@@ -108,7 +114,7 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
                         d_out_scores, d_out_rows, st);
   }
   // scan path: TF32 requests with few queries are served by the exact fp32 scan
-  return search_scan(s, prec == PVDB_PREC_BF16, d_qn, nq, k, d_pref, d_out_scores, d_out_rows, st);
+  return search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st);
 }
 
 }  // namespace pvdb

@@ -33,11 +33,12 @@ __device__ __forceinline__ uint64_t load_key(const uint64_t* p) {
 }
 
 template <bool GLOBAL>
-__device__ __forceinline__ void merge_list(WarpList<kSlots>& L, uint64_t& thr, const uint64_t* src, int k,
+__device__ __forceinline__ void merge_list(WarpList<kSlots>& L, uint64_t& thr, const uint64_t* src, int n, int k,
                                            int lane) {
-  for (int base = 0; base < k; base += 32) {
+  // src: descending list of n keys; k: rank whose key is the admission threshold
+  for (int base = 0; base < n; base += 32) {
     const int e = base + lane;
-    const uint64_t v = (e < k) ? load_key<GLOBAL>(src + e) : 0ull;
+    const uint64_t v = (e < n) ? load_key<GLOBAL>(src + e) : 0ull;
     unsigned m = __ballot_sync(0xffffffffu, v > thr);
     if (m == 0) break;  // lists are descending: nothing further can qualify
     while (m) {
@@ -99,7 +100,32 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   const int gi = lane / LPR;
   const int k = p.k;
 
-  for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = p.query[i];
+  if (p.raw_query != nullptr) {
+    // Fused query preparation (picovdb/pico_vdb.py:584-591): every block normalises the raw query
+    // itself -- fp32 sum of squares, fp32 norm, IEEE division, zero query -> e0 -- which saves a
+    // kernel launch and a round trip through HBM on the single-query path.
+    __shared__ float s_part[kScanWarps];
+    float ss = 0.f;
+    for (int i = tid; i < p.query_floats; i += kScanThreads) {
+      const float x = (i < p.dim) ? p.raw_query[i] : 0.f;
+      sq[i] = x;
+      ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) s_part[warp] = ss;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w2 = 0; w2 < kScanWarps; ++w2) tot += static_cast<double>(s_part[w2]);
+    const float nrm = static_cast<float>(sqrt(tot));
+    for (int i = tid; i < p.query_floats; i += kScanThreads) {
+      const float x = sq[i];
+      sq[i] = (nrm == 0.f) ? (i == 0 ? 1.f : 0.f) : __fdiv_rn(x, nrm);
+    }
+  } else {
+    for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = p.query[i];
+  }
   __syncthreads();
   const float4* sq4 = reinterpret_cast<const float4*>(sq);
 
@@ -185,7 +211,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   store_list(L, slist + warp * k, k, lane);
   __syncthreads();
   if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, lane);
+    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
     store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
     __threadfence();
     __syncwarp();
@@ -201,13 +227,41 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   __threadfence();
   L.clear();
   thr = 0ull;
-  for (int b = warp; b < static_cast<int>(gridDim.x); b += kScanWarps)
-    merge_list<true>(L, thr, p.partial + static_cast<size_t>(b) * k, k, lane);
+  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
+  // together so the L2 round trips overlap; a list whose whole head qualified continues through
+  // the general path.
+  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += kScanWarps * 8) {
+    uint64_t head[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * kScanWarps;
+      head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
+                    ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
+                    : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * kScanWarps;
+      if (b >= static_cast<int>(gridDim.x)) break;
+      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
+      const bool head_all = (m == 0xffffffffu);
+      while (m) {
+        const int srcl = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t x = shfl_u64(head[j], srcl);
+        if (x > thr) {
+          L.insert(x, lane);
+          thr = L.get(k - 1);
+        }
+      }
+      if (head_all && k > 32) merge_list<true>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
+    }
+  }
   __syncthreads();  // everyone is done reading slist from the first merge
   store_list(L, slist + warp * k, k, lane);
   __syncthreads();
   if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, lane);
+    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) {
       const int e = s * 32 + lane;

@@ -13,6 +13,8 @@ struct ScanParams {
   const uint32_t* active;    // active bitmap (always present)
   const uint32_t* prefilter; // optional second bitmap, ANDed with `active`
   const float* query;        // normalised query, padded with zeros to a multiple of 8 floats
+  const float* raw_query;    // if non-null: raw query of `dim` floats, normalised inside the kernel
+  int dim;
   int query_floats;          // padded query length
   int k;                     // 1 .. kFusedK for this pass
   const uint64_t* upper;     // only keys strictly below *upper qualify (paging); NULL = no bound
