@@ -103,6 +103,22 @@ __device__ __forceinline__ void decode_visit(const BatchParams& p, int64_t v, in
   }
 }
 
+// Cluster variant (CL = 2): the two CTAs of a cluster always work on the same database tile and on
+// two consecutive query tiles, so the tile's K slices can be fetched once and multicast to both.
+// A cluster-visit is (t, query-tile pair); returns false for the padding query tile of an odd count.
+template <int CL>
+__device__ __forceinline__ bool decode_unit_visit(const BatchParams& p, int64_t v, uint32_t cta_rank, int& t, int& qt) {
+  if constexpr (CL == 1) {
+    decode_visit(p, v, t, qt);
+    return true;
+  } else {
+    const int n_qp = (p.q_tiles + CL - 1) / CL;
+    t = static_cast<int>(v / n_qp);
+    qt = static_cast<int>(v - static_cast<int64_t>(t) * n_qp) * CL + static_cast<int>(cta_rank);
+    return qt < p.q_tiles;
+  }
+}
+
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -138,6 +154,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask` and
+// completes bytes on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -308,7 +342,7 @@ __device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float
 }
 
 // ---------------------------------------------------------------------------- the GEMM + top-k kernel
-template <bool BF16, int NI>
+template <bool BF16, int NI, int CL>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                   const BatchParams p) {
@@ -325,6 +359,11 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const int unit_id = static_cast<int>(blockIdx.x) / CL;   // cluster index (== CTA index when CL == 1)
+  const int n_units = static_cast<int>(gridDim.x) / CL;
+  constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
@@ -334,7 +373,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);  // every CTA that receives the multicast must release the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -350,11 +389,12 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * p.q_tiles;
+  const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * ((p.q_tiles + CL - 1) / CL);
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -364,16 +404,23 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
-      for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+      for (int64_t v = unit_id; v < n_visits; v += n_units) {
         int t, qt;
-        decode_visit(p, v, t, qt);
+        decode_unit_visit<CL>(p, v, cta_rank, t, qt);  // a padding query tile loads zeros (out of bounds)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
           const uint32_t b_dst = a_dst + kStageABytes;
           mbar_expect_tx(full_bar(stage), kStageBytes);
           tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
-          tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
+          if constexpr (CL == 1) {
+            tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
+          } else {
+            // this CTA fetches its 1/CL share of the tile's rows and multicasts it to the cluster
+            constexpr int kShareRows = kBN / CL;
+            tma_load_2d_mc(b_dst + cta_rank * (kStageBBytes / CL), &map_db, full_bar(stage), kb * kElemsPerStage,
+                           (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * kShareRows, kClusterMask);
+          }
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -389,7 +436,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+      for (int64_t v = unit_id; v < n_visits; v += n_units) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
@@ -405,7 +452,9 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
                        (kb | j) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(stage));  // ring slot reusable once these MMAs retire
+          // ring slot reusable once these MMAs retire (in every CTA the multicast writes to)
+          if constexpr (CL == 1) tcgen05_commit(empty_bar(stage));
+          else tcgen05_commit_mc(empty_bar(stage), kClusterMask);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -436,9 +485,21 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t v = blockIdx.x; v < n_visits; v += gridDim.x) {
+    for (int64_t v = unit_id; v < n_visits; v += n_units) {
       int t, qt;
-      decode_visit(p, v, t, qt);
+      if (!decode_unit_visit<CL>(p, v, cta_rank, t, qt)) {
+        // padding query tile of an odd count: nothing to select, just recycle the accumulator
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+        continue;
+      }
       uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
       uint64_t* pool = warp_pools + static_cast<size_t>(lane) * p.pool_cap;
       float thr = s_thr[qt * kBM + ql];
@@ -528,7 +589,9 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  // with clusters nobody may leave while a peer can still multicast into, or signal, this CTA
+  if constexpr (CL > 1) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -690,18 +753,30 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
   return PVDB_OK;
 }
 
-template <bool BF16>
+template <bool BF16, int CL>
 static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p, int grid,
                           cudaStream_t st) {
   auto run = [&](auto kern) -> int {
     PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmem)));
-    kern<<<grid, kBatchThreads, kBatchSmem, st>>>(mq, mdb, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kBatchThreads);
+    cfg.dynamicSmemBytes = kBatchSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PVDB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mdb, p));
     PVDB_LAUNCH_CHECK();
     return PVDB_OK;
   };
   switch (p.pool_cap) {
-    case 128: return run(batch_topk_kernel<BF16, 4>);
-    default: return run(batch_topk_kernel<BF16, 8>);
+    case 128: return run(batch_topk_kernel<BF16, 4, CL>);
+    default: return run(batch_topk_kernel<BF16, 8, CL>);
   }
 }
 
@@ -714,9 +789,18 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   const int k_sel = k + (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0);
   if (k_sel > kMaxSel) return fail(PVDB_ERR_UNSUPPORTED, "batch: k=%d too large for the fused tensor-core path", k);
 
-  CUtensorMap mdb;
-  if (use_bf16) PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
-  else PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
+  // Two query tiles or more: 2-CTA clusters share every database tile through TMA multicast (each
+  // CTA fetches half of the tile's rows), which cuts the L2 -> shared-memory traffic per CTA from
+  // 48 KB to 32 KB per K block.  A single query tile has nobody to share with.
+  const bool cluster_ok = getenv("PVDB_BATCH_NO_CLUSTER") == nullptr;
+  CUtensorMap mdb, mdb_half;
+  if (use_bf16) {
+    PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
+    PVDB_TRY(encode_map(&mdb_half, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN / 2));
+  } else {
+    PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
+    PVDB_TRY(encode_map(&mdb_half, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN / 2));
+  }
 
   const int64_t max_q = static_cast<int64_t>(kMaxQTiles) * kBM;
   const int total_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
@@ -745,7 +829,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     if (const char* e = getenv("PVDB_BATCH_SAMPLE")) sample_tiles = atoi(e) > 0 ? total_tiles / atoi(e) : 0;
     if (static_cast<int64_t>(sample_tiles) * p.q_tiles < 4 * kNumSMs) sample_tiles = 0;  // too small to pay off
 
-    const int grid_max = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(total_tiles) * p.q_tiles, kNumSMs));
+    const int grid_max = kNumSMs;  // pools / flags are sized for a full grid
     const size_t pool_bytes = static_cast<size_t>(grid_max) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
     const size_t touched_bytes = (static_cast<size_t>(grid_max) * p.q_tiles + 255) & ~size_t(255);
     const size_t thr_bytes = (static_cast<size_t>(nq) * sizeof(uint32_t) + 255) & ~size_t(255);
@@ -768,11 +852,18 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       p.tile_begin = tile_begin;
       p.n_tiles = n_tiles;
       p.init_thr = thr_in;
-      const int64_t n_visits = static_cast<int64_t>(n_tiles) * p.q_tiles;
-      const int grid = static_cast<int>(std::min<int64_t>(n_visits, kNumSMs));
+      const bool cluster = cluster_ok && p.q_tiles >= 2;
+      const int cl = cluster ? 2 : 1;
+      const int64_t n_visits = static_cast<int64_t>(n_tiles) * ((p.q_tiles + cl - 1) / cl);
+      const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, kNumSMs / cl));
       PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
-      if (use_bf16) PVDB_TRY(launch_batch_t<true>(mq, mdb, p, grid, st));
-      else PVDB_TRY(launch_batch_t<false>(mq, mdb, p, grid, st));
+      if (cluster) {
+        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2>(mq, mdb_half, p, grid, st)));
+        else PVDB_TRY((launch_batch_t<false, 2>(mq, mdb_half, p, grid, st)));
+      } else {
+        if (use_bf16) PVDB_TRY((launch_batch_t<true, 1>(mq, mdb, p, grid, st)));
+        else PVDB_TRY((launch_batch_t<false, 1>(mq, mdb, p, grid, st)));
+      }
       finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
           p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
           static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
