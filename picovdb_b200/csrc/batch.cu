@@ -77,6 +77,9 @@ struct BatchParams {
   uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
   uint32_t* shared_thr;  // [nq] ordered-int image of the best published k_sel-th score (zeroed)
   int tile_begin;        // first database tile of this launch (n_tiles counts from here)
+  int visit_stride;      // 0: units stride by their count (every unit meets many query tiles);
+                         // else a multiple of the query-tile(-pair) count: unit u keeps ONE query tile
+                         // and units >= visit_stride stay idle (cheap cold start for the sample pass)
   const float* init_thr; // optional [nq]: a proven lower bound of each query's k_sel-th best score
   int q_group;         // query tiles that share a database tile back to back (visit order)
 };
@@ -363,6 +366,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   const int unit_id = static_cast<int>(blockIdx.x) / CL;   // cluster index (== CTA index when CL == 1)
   const int n_units = static_cast<int>(gridDim.x) / CL;
+  const int64_t v_step = p.visit_stride > 0 ? p.visit_stride : n_units;
   constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -395,6 +399,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * ((p.q_tiles + CL - 1) / CL);
+  const int64_t v_first = unit_id < v_step ? unit_id : n_visits;  // surplus units of a pinned schedule idle
 
   if (warp == 0) {
     // ======================= TMA producer =======================
@@ -404,7 +409,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
-      for (int64_t v = unit_id; v < n_visits; v += n_units) {
+      for (int64_t v = v_first; v < n_visits; v += v_step) {
         int t, qt;
         decode_unit_visit<CL>(p, v, cta_rank, t, qt);  // a padding query tile loads zeros (out of bounds)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
@@ -436,7 +441,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int64_t v = unit_id; v < n_visits; v += n_units) {
+      for (int64_t v = v_first; v < n_visits; v += v_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
@@ -485,7 +490,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t v = unit_id; v < n_visits; v += n_units) {
+    for (int64_t v = v_first; v < n_visits; v += v_step) {
       int t, qt;
       if (!decode_unit_visit<CL>(p, v, cta_rank, t, qt)) {
         // padding query tile of an odd count: nothing to select, just recycle the accumulator
@@ -817,8 +822,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     p.pool_cap = k_sel <= 32 ? 128 : 256;
     p.active = static_cast<const uint32_t*>(s->active.ptr);
     p.prefilter = d_pref;
-    p.q_group = std::min(p.q_tiles, kDefaultQGroup);
-    if (const char* e = getenv("PVDB_BATCH_QGROUP")) p.q_group = std::max(1, std::min(p.q_tiles, atoi(e)));
+    p.q_group = p.q_tiles;  // pure tile-major visit numbering
 
     // Sample pass: the first 1/16 of the tiles is searched on its own; the k_sel-th best score it
     // finds for a query is a proven lower bound of that query's final k_sel-th best, so the main
@@ -848,7 +852,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
 
     auto run_pass = [&](int tile_begin, int n_tiles, const float* thr_in, const uint64_t* carry_in, uint64_t* carry_out,
-                        float* thr_out) -> int {
+                        float* thr_out, bool pin_query_tiles) -> int {
       p.tile_begin = tile_begin;
       p.n_tiles = n_tiles;
       p.init_thr = thr_in;
@@ -856,6 +860,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       const int cl = cluster ? 2 : 1;
       const int64_t n_visits = static_cast<int64_t>(n_tiles) * ((p.q_tiles + cl - 1) / cl);
       const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, kNumSMs / cl));
+      // pinned schedule: stride = (query-tile pairs) x (units per pair), so a unit never changes pair
+      const int n_qp = (p.q_tiles + cl - 1) / cl, n_units = grid / cl;
+      p.visit_stride = (pin_query_tiles && n_units >= n_qp) ? n_qp * (n_units / n_qp) : 0;
       PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
       if (cluster) {
         if (use_bf16) PVDB_TRY((launch_batch_t<true, 2>(mq, mdb_half, p, grid, st)));
@@ -872,10 +879,10 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       return PVDB_OK;
     };
     if (sample_tiles > 0) {
-      PVDB_TRY(run_pass(0, sample_tiles, nullptr, nullptr, carry, init_thr));
-      PVDB_TRY(run_pass(sample_tiles, total_tiles - sample_tiles, init_thr, carry, nullptr, nullptr));
+      PVDB_TRY(run_pass(0, sample_tiles, nullptr, nullptr, carry, init_thr, true));
+      PVDB_TRY(run_pass(sample_tiles, total_tiles - sample_tiles, init_thr, carry, nullptr, nullptr, false));
     } else {
-      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr));
+      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr, false));
     }
   }
   return PVDB_OK;
