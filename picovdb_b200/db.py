@@ -145,6 +145,71 @@ class _RWLock:
             self.release_write()
 
 
+class _ColumnIndex:
+    """Columnar mirror of one metadata key: ``codes[row]`` is the dictionary code of
+    ``docs[row].get(key)`` (-1 for deleted slots).  It turns the reference's per-query Python loop
+    over candidate docs for ``{key: value}`` / ``{key: {"$in": [...]}}`` filters
+    (pico_vdb.py:615-638; 21 ms at 100k rows) into one vectorised compare.  Built lazily on the
+    first filter that names the key and maintained incrementally by upsert / delete / vacuum.
+    Python equality semantics are kept because codes come from a dict lookup (1 == 1.0 == True)."""
+
+    def __init__(self, key: str, docs: list) -> None:
+        self.key = key
+        self.vocab: dict[Any, int] = {}
+        self.codes = np.full(max(len(docs), 16), -1, dtype=np.int32)
+        self.n = len(docs)
+        self.ok = True
+        for row, doc in enumerate(docs):
+            if doc is not None:
+                self.set(row, doc)
+
+    def _code(self, value: Any, create: bool) -> int:
+        try:
+            code = self.vocab.get(value)
+            if code is None and create:
+                code = self.vocab[value] = len(self.vocab)
+        except TypeError:  # unhashable metadata value: this key falls back to the Python loop
+            self.ok = False
+            return -1
+        return -1 if code is None else code
+
+    def set(self, row: int, doc: Optional[dict]) -> None:
+        if row >= self.codes.shape[0]:
+            grown = np.full(max(row + 1, 2 * self.codes.shape[0]), -1, dtype=np.int32)
+            grown[: self.n] = self.codes[: self.n]
+            self.codes = grown
+        self.n = max(self.n, row + 1)
+        self.codes[row] = -1 if doc is None else self._code(doc.get(self.key), True)
+
+    def resize(self, n: int) -> None:
+        if n > self.n:
+            self.set(n - 1, None)
+        self.n = n
+
+    def match(self, values, n: int) -> Optional[np.ndarray]:
+        """bool mask over rows [0, n) whose value equals one of ``values``; None if unsupported."""
+        self.resize(n)
+        wanted = []
+        for v in values:
+            c = self._code(v, False)
+            if not self.ok:
+                return None
+            if c >= 0:
+                wanted.append(c)
+        codes = self.codes[:n]
+        if not wanted:
+            return np.zeros(n, dtype=bool)
+        if len(wanted) == 1:
+            return codes == wanted[0]
+        return np.isin(codes, np.asarray(wanted, dtype=np.int32))
+
+    def reindex(self, keep: list[int]) -> None:
+        kept = self.codes[np.asarray(keep, dtype=np.int64)] if keep else np.empty(0, np.int32)
+        self.codes = np.full(max(len(keep), 16), -1, dtype=np.int32)
+        self.codes[: len(keep)] = kept
+        self.n = len(keep)
+
+
 def _default_engine_factory(dim: int, **kw):
     """The product engine: CUDA or nothing."""
     from .engine import DeviceStore
@@ -235,6 +300,7 @@ class PicoVectorDB:
             fixed_capacity=capacity is not None,
         )
         self._host_cache: Optional[np.ndarray] = None  # lazily downloaded copy behind `_vectors`
+        self._columns: dict[str, _ColumnIndex] = {}    # metadata key -> columnar index (lazy)
         self._load_or_init()
 
     # ------------------------------------------------------------------ host mirror of the matrix
@@ -260,7 +326,7 @@ class PicoVectorDB:
             with open(ids_file, "r", encoding="utf-8") as f:
                 self._ids = json.load(f)
             count = len(self._ids)
-            vectors = self._read_vectors(vecs_file, count)
+            vectors = self._read_vectors(vecs_file, count)  # memory-mapped; streamed to the device below
             if os.path.exists(meta_file):
                 with open(meta_file, "r", encoding="utf-8") as f:
                     meta_json = json.load(f)
@@ -277,8 +343,13 @@ class PicoVectorDB:
             if self._id2idx:
                 self._active_indices = np.fromiter(self._id2idx.values(), dtype=np.int64)
                 active[self._active_indices] = True
-            if count:
-                self._engine.upload(vectors, 0, active)
+            # stream the matrix to the device in row blocks (multiples of 32 rows so every block's
+            # slice of the active bitmap starts on a word boundary); the file is only mapped, so a
+            # store larger than host RAM still loads
+            step = max(32, ((64 << 20) // (self.dim * 4)) // 32 * 32)
+            for r0 in range(0, count, step):
+                r1 = min(count, r0 + step)
+                self._engine.upload(np.ascontiguousarray(vectors[r0:r1], dtype=Float), r0, active[r0:r1])
             logger.info("Loaded %d active / %d total vectors", len(self._id2idx), count)
         else:
             if self._capacity is not None:
@@ -293,14 +364,15 @@ class PicoVectorDB:
 
     def _read_vectors(self, vecs_file: str, count: int) -> np.ndarray:
         try:
-            arr = np.load(vecs_file)
+            arr = np.load(vecs_file, mmap_mode="r")
         except (ValueError, OSError):
             # headerless pre-allocated file written by `capacity=` + `use_memmap=True`
             arr = np.fromfile(vecs_file, dtype=Float)
             if arr.size != count * self.dim:
                 raise
             arr = arr.reshape(count, self.dim)
-        arr = _to_c_f32(arr)
+        if arr.dtype != Float:
+            arr = _to_c_f32(arr)
         if arr.shape != (count, self.dim):
             raise ValueError(
                 f"stored matrix has shape {arr.shape}, expected ({count}, {self.dim})"
@@ -319,7 +391,7 @@ class PicoVectorDB:
             try:
                 with open(tmp_ids, "w", encoding="utf-8") as f:
                     json.dump(self._ids, f, ensure_ascii=False)
-                np.save(tmp_vecs_base, self._vectors)
+                self._write_vectors(tmp_vecs)
                 with open(tmp_meta, "w", encoding="utf-8") as f:
                     json.dump(
                         {"embedding_dim": self.dim, "data": self._docs, "additional_data": self._additional},
@@ -337,6 +409,24 @@ class PicoVectorDB:
                             os.remove(tmp)
                         except OSError:
                             pass
+
+    def _write_vectors(self, path: str) -> None:
+        """Write the ``.npy`` file (same header as ``np.save``) in row blocks straight from the
+        device, so saving never needs a second full copy of the matrix in host memory."""
+        n = len(self._ids)
+        if n == 0 or self._host_cache is not None:
+            with open(path, "wb") as f:
+                np.save(f, self._vectors)
+            return
+        from numpy.lib.format import open_memmap
+
+        out = open_memmap(path, mode="w+", dtype=Float, shape=(n, self.dim))
+        step = max(1, (64 << 20) // (self.dim * 4))
+        for r0 in range(0, n, step):
+            r1 = min(n, r0 + step)
+            out[r0:r1] = self._engine.download(r0, r1 - r0)
+        out.flush()
+        del out
 
     def flush(self) -> None:
         """No-op: the store is device resident; ``save()`` writes the files."""
@@ -414,6 +504,8 @@ class PicoVectorDB:
                         new_active.append(row)
                         self._id2idx[item_id] = row
                         report["insert"].append(item_id)
+                    for col in self._columns.values():
+                        col.set(row, meta)
                     pos = slot_of_row.get(row)
                     if pos is None:
                         slot_of_row[row] = len(staged)
@@ -467,6 +559,9 @@ class PicoVectorDB:
             else:
                 self._docs.extend({**d, K_ID: i} for d, i in zip(docs, new_ids))
             self._id2idx.update(zip(new_ids, range(row0, row0 + n)))
+            for col in self._columns.values():
+                for row in range(row0, row0 + n):
+                    col.set(row, self._docs[row])
             add = np.arange(row0, row0 + n, dtype=np.int64)
             self._active_indices = np.append(self._active_indices, add) if self._active_indices.size else add
             return new_ids
@@ -488,6 +583,8 @@ class PicoVectorDB:
                 row = self._id2idx.pop(_id, None)
                 if row is not None:
                     self._docs[row] = None
+                    for col in self._columns.values():
+                        col.set(row, None)
                     self._free.append(row)
                     rows.append(row)
                     removed.append(_id)
@@ -538,6 +635,17 @@ class PicoVectorDB:
             return mask
         if isinstance(where, dict) and len(where) == 1:
             ((key, val),) = where.items()
+            is_in = isinstance(val, dict) and set(val.keys()) == {"$in"}
+            col = self._columns.get(key) if isinstance(key, str) else None
+            if col is None and isinstance(key, str):
+                col = self._columns[key] = _ColumnIndex(key, docs)
+            if col is not None and col.ok:
+                try:
+                    hit = col.match(set(val["$in"]) if is_in else (val,), n)
+                except TypeError:  # unhashable filter value
+                    hit = None
+                if hit is not None:
+                    return hit if ids is None else (hit & mask)
             if isinstance(val, dict) and set(val.keys()) == {"$in"}:
                 wanted = set(val["$in"])
                 keep = [i for i in base_rows if docs[i] is not None and docs[i].get(key) in wanted]
@@ -674,6 +782,8 @@ class PicoVectorDB:
             self._invalidate()
             self._ids = [self._ids[i] for i in keep]
             self._docs = [self._docs[i] for i in keep]
+            for col in self._columns.values():
+                col.reindex(keep)
             self._id2idx = {_id: i for i, _id in enumerate(self._ids)}
             self._active_indices = np.arange(len(self._ids), dtype=np.int64)
             self._free = []
