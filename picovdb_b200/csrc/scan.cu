@@ -139,25 +139,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
   const int row_chunks = p.row_chunks;
 
-  // The bitmap word of a step is fetched one step ahead: consecutive steps of a warp are
-  // total_warps * RPW rows apart, i.e. in different cache lines of the bitmap, and a warp whose
-  // rows are mostly filtered out would otherwise pay one L2 round trip per (skipped) step.
-  const int64_t step0 = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp;
-  uint32_t w_next = 0u;
-  if (step0 < n_steps) {
-    w_next = __ldg(p.active + ((step0 * RPW) >> 5));
-    if (p.prefilter) w_next &= __ldg(p.prefilter + ((step0 * RPW) >> 5));
-  }
-  for (int64_t step = step0; step < n_steps; step += total_warps) {
+  // (Fetching the bitmap word one step ahead was measured on the B200 and lost: +15 % on the bf16
+  // scan from the extra live registers, no gain on the filtered cases.)
+  for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; step < n_steps; step += total_warps) {
     const int64_t base = step * RPW;
-    uint32_t w = w_next;
-    {
-      const int64_t nstep = step + total_warps;
-      if (nstep < n_steps) {
-        w_next = __ldg(p.active + ((nstep * RPW) >> 5));
-        if (p.prefilter) w_next &= __ldg(p.prefilter + ((nstep * RPW) >> 5));
-      }
-    }
+    uint32_t w = __ldg(p.active + (base >> 5));
+    if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
     w >>= (base & 31);
     if constexpr (RPW < 32) w &= (1u << RPW) - 1u;
     if (w == 0u) continue;  // every row of this step is deleted / filtered out: read nothing
