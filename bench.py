@@ -51,25 +51,38 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_000_000)
-    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, BASELINE configs[1]): 1M x 1024 fp32; c5: 100M x 384 bf16 mirror only "
+                         "(the north-star target config, single queries), sharded over the ranks")
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries-per-step", type=int, default=32)
     ap.add_argument("--cpu-queries", type=int, default=24, help="single queries timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.workload == "c5":
+        args.rows = args.rows or 100_000_000
+        args.dim = args.dim or 384
+        args.store_dtype, args.precision, args.elem_bytes = "bf16", "bf16", 2
+    else:
+        args.rows = args.rows or 1_000_000
+        args.dim = args.dim or 1024
+        args.store_dtype, args.precision, args.elem_bytes = "f32", "f32", 4
+    return args
 
 
 def workload_config(args, world):
     return {
-        "workload": f"C2: {args.rows}x{args.dim} fp32 unit-norm rows, single-query top-{args.k} (HBM-bound scan)",
+        "workload": (f"{args.workload.upper()}: {args.rows}x{args.dim} {args.store_dtype} unit-norm rows, "
+                     f"single-query top-{args.k} (HBM-bound scan)"),
         "rows": args.rows,
         "dim": args.dim,
         "k": args.k,
         "queries_per_step": args.queries_per_step,
         "sharding": f"rows/{world} contiguous per rank" if world > 1 else "none",
         "exchange": "one all-gather + merge kernel per step" if world > 1 else "none",
-        "l2": "inputs (4.1 GB per pass) larger than L2 (126 MB): no flush needed",
+        "l2": f"inputs ({args.rows * args.dim * args.elem_bytes / world / 1e9:.1f} GB per pass per GPU) larger than L2 (126 MB): no flush needed",
         "seeds": {"db": 123, "queries": 99},
     }
 
@@ -163,6 +176,8 @@ def cpu_rows_that_fit(args) -> int:
     except Exception:
         avail = 16 << 30
     need = args.rows * args.dim * 4
+    if args.workload == "c5":
+        return min(args.rows, 2_000_000)  # the reference holds fp32 only: 100M x 384 = 154 GB; bounded sample
     if need * 1.3 < avail:
         return args.rows
     return max(1, int(avail / 1.3 / (args.dim * 4)))
@@ -187,7 +202,7 @@ def time_oracle(args, n_queries: int, warm: int = 2):
     scale = rows / args.rows  # < 1 only when the full matrix does not fit in host RAM
     sample = f"{n_queries} single queries over {rows}x{args.dim} fp32 on the host"
     if rows != args.rows:
-        sample += f" (host RAM bound; time scaled linearly to {args.rows} rows)"
+        sample += f" (bounded sample; time scaled linearly to {args.rows} rows)"
         per_query = per_query / scale
     return per_query, sample, times
 
@@ -262,7 +277,8 @@ def run_b200(args, world, rank, local_rank):
 
     r0, r1 = shard_range(args.rows, world, rank)
     n_local = r1 - r0
-    store = DeviceStore(args.dim, device=local_rank, reserve_rows=max(n_local, 1))
+    store = DeviceStore(args.dim, device=local_rank, reserve_rows=max(n_local, 1),
+                        keep_f32=args.store_dtype == "f32", bf16_mirror=args.store_dtype == "bf16")
     gen = torch.Generator(device=dev).manual_seed(123 + rank)
     chunk = 131072
     stream = torch.cuda.current_stream().cuda_stream
@@ -283,7 +299,7 @@ def run_b200(args, world, rank, local_rank):
 
     def step_device(i):
         sl = q_dev[(i % (n_pool // qps)) * qps:][:qps]
-        return sharded.search_dev(sl, k, precision="f32")
+        return sharded.search_dev(sl, k, precision=args.precision)
 
     # ---- sanity: results sorted, rows valid, all ranks agree (full parity lives in tests/)
     s0, r0_ = step_device(0)
@@ -317,8 +333,8 @@ def run_b200(args, world, rank, local_rank):
         base = (i % (n_pool // qps)) * qps
         out = None
         for j in range(qps):
-            out = sharded.search(q_np[base + j: base + j + 1], k, precision="f32") if world > 1 else \
-                store.search(q_np[base + j: base + j + 1], k, precision="f32")
+            out = sharded.search(q_np[base + j: base + j + 1], k, precision=args.precision) if world > 1 else \
+                store.search(q_np[base + j: base + j + 1], k, precision=args.precision)
         return out
 
     for i in range(min(args.warmup, 3)):
@@ -338,14 +354,14 @@ def run_b200(args, world, rank, local_rank):
     out_r = torch.empty(k, dtype=torch.int64, device=dev)
     n_scan = 50
     for j in range(5):
-        store.search_dev(qn_dev[j].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32",
+        store.search_dev(qn_dev[j].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision=args.precision,
                          normalized=True, stream=stream)
     torch.cuda.synchronize()
     l0 = N.kernel_launches()
     ev0.record()
     for j in range(n_scan):
-        store.search_dev(qn_dev[j % n_qn].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32",
-                         normalized=True, stream=stream)
+        store.search_dev(qn_dev[j % n_qn].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(),
+                         precision=args.precision, normalized=True, stream=stream)
     ev1.record()
     torch.cuda.synchronize()
     assert N.kernel_launches() - l0 == n_scan, "roofline loop must launch exactly one kernel per query"
@@ -361,7 +377,7 @@ def run_b200(args, world, rank, local_rank):
         value = n_queries / (dev_ms / 1e3)
         e2e_value = n_queries / (e2e_ms / 1e3)
         peak, peak_src = load_peaks()
-        algo_bytes = n_local * args.dim * 4 + n_local / 8
+        algo_bytes = n_local * args.dim * args.elem_bytes + n_local / 8
         achieved = algo_bytes / (scan_ms / 1e3) / 1e9
         line = {
             "metric": METRIC,
@@ -374,7 +390,7 @@ def run_b200(args, world, rank, local_rank):
             "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "f32",
+            "dtype": args.store_dtype,
             "data": "synthetic",
             "config": workload_config(args, world),
             "e2e": {
@@ -387,7 +403,7 @@ def run_b200(args, world, rank, local_rank):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm",
-                "kernel": "scan_topk_kernel<fp32> (masked GEMV + fused top-k)",
+                "kernel": f"scan_topk_kernel<{args.store_dtype}> (masked GEMV + fused top-k)",
                 "achieved": achieved,
                 "peak": peak,
                 "unit": "GB/s",
@@ -395,7 +411,7 @@ def run_b200(args, world, rank, local_rank):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo_bytes,
                 "us_per_launch": scan_ms * 1e3,
-                "traffic": load_traffic(f"scan_f32_{args.rows}x{args.dim}") if world == 1 else None,
+                "traffic": load_traffic(f"scan_{args.store_dtype}_{args.rows}x{args.dim}") if world == 1 else None,
             },
             "clocks": clocks,
         }
