@@ -53,6 +53,7 @@ extern "C" {
 /* search flags */
 #define PVDB_SEARCH_QUERIES_NORMALIZED 0x100 /* skip the query L2-normalisation (pico_vdb.py:584-591) */
 #define PVDB_SEARCH_NO_RESCORE 0x200         /* tensor-core paths: return the low-precision scores */
+#define PVDB_SEARCH_SCAN_ONLY 0x400          /* answer every query with its own HBM scan pass (no batching) */
 
 typedef struct pvdb_store pvdb_store_t;
 

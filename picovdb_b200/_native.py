@@ -26,6 +26,7 @@ STORE_FIXED_CAPACITY = 0x4
 PREC_AUTO, PREC_F32, PREC_TF32, PREC_BF16 = 0, 1, 2, 3
 SEARCH_QUERIES_NORMALIZED = 0x100
 SEARCH_NO_RESCORE = 0x200
+SEARCH_SCAN_ONLY = 0x400
 
 PRECISIONS = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 

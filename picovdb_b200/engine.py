@@ -173,6 +173,7 @@ class DeviceStore:
         precision: str = "auto",
         normalized: bool = False,
         rescore: bool = True,
+        scan_only: bool = False,
     ) -> tuple[np.ndarray, np.ndarray]:
         """(Q, dim) fp32 queries -> (scores (Q, k) f32 descending, rows (Q, k) int64).
 
@@ -196,13 +197,16 @@ class DeviceStore:
             flags |= N.SEARCH_QUERIES_NORMALIZED
         if not rescore:
             flags |= N.SEARCH_NO_RESCORE
+        if scan_only:
+            flags |= N.SEARCH_SCAN_ONLY
         scores = np.empty((nq, k), dtype=np.float32)
         rows = np.empty((nq, k), dtype=np.int64)
         N.check(self._lib.pvdb_search(self.handle, _ptr(q), nq, k, _ptr(bits), flags, _ptr(scores), _ptr(rows)))
         return scores, rows
 
     def search_dev(self, d_queries: int, nq: int, k: int, d_scores: int, d_rows: int, d_prefilter: int = 0,
-                   precision: str = "auto", normalized: bool = False, rescore: bool = True, stream: int = 0) -> None:
+                   precision: str = "auto", normalized: bool = False, rescore: bool = True, stream: int = 0,
+                   scan_only: bool = False) -> None:
         """Device pointers in / out; only enqueues work on ``stream`` (a ``cudaStream_t`` as int;
         0 = CUDA's legacy default stream, which is also torch's default stream)."""
         flags = N.PRECISIONS[precision]
@@ -210,6 +214,8 @@ class DeviceStore:
             flags |= N.SEARCH_QUERIES_NORMALIZED
         if not rescore:
             flags |= N.SEARCH_NO_RESCORE
+        if scan_only:
+            flags |= N.SEARCH_SCAN_ONLY
         N.check(
             self._lib.pvdb_search_dev(
                 self.handle, C.c_void_p(d_queries), int(nq), int(k), C.c_void_p(d_prefilter or None), flags,

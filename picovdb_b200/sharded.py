@@ -75,7 +75,7 @@ class ShardedSearch:
         return b
 
     def search_dev(self, d_queries: torch.Tensor, k: int, precision: str = "auto", normalized: bool = False,
-                   d_prefilter: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+                   d_prefilter: Optional[torch.Tensor] = None, scan_only: bool = False) -> tuple[torch.Tensor, torch.Tensor]:
         """CUDA tensors in (``(Q, dim)`` fp32), CUDA tensors out; enqueued on torch's current stream.
         The returned tensors are reused by the next call with the same (Q, k)."""
         from .engine import merge_topk_dev
@@ -89,7 +89,7 @@ class ShardedSearch:
         self.local.search_dev(
             d_queries.data_ptr(), nq, k, loc.data_ptr() + n_out * 8, loc.data_ptr(),
             d_prefilter=d_prefilter.data_ptr() if d_prefilter is not None else 0,
-            precision=precision, normalized=normalized, stream=stream,
+            precision=precision, normalized=normalized, stream=stream, scan_only=scan_only,
         )
         if self.world == 1:
             gathered = loc
