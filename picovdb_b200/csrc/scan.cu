@@ -11,6 +11,7 @@
 //
 // HBM roofline: algorithmic bytes per query = scored_rows * dim * sizeof(T) + rows/8 (bitmap).
 #include <algorithm>
+#include <cstdlib>
 
 #include "scan.cuh"
 
@@ -83,7 +84,7 @@ __device__ __forceinline__ float dot_chunk_bf16(const uint4& v, const float4& q0
 
 // LPR lanes cooperate on one row; each lane keeps CH 16-byte loads of R rows in flight
 // (CH * R == 8 -> eight independent 128-bit loads per lane per step).
-template <bool BF16, int LPR, int CH>
+template <bool BF16, int LPR, int CH, bool SPARSE>
 __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kernel(const ScanParams p) {
   constexpr int G = 32 / LPR;  // row groups per warp
   constexpr int R = 8 / CH;    // rows in flight per group
@@ -135,28 +136,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   uint64_t thr = 0ull;
 
   const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanWarps;
-  const int64_t n_steps = (p.n_rows + RPW - 1) / RPW;
   const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
   const int row_chunks = p.row_chunks;
 
-  // (Fetching the bitmap word one step ahead was measured on the B200 and lost: +15 % on the bf16
-  // scan from the extra live registers, no gain on the filtered cases.)
-  for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; step < n_steps; step += total_warps) {
-    const int64_t base = step * RPW;
-    uint32_t w = __ldg(p.active + (base >> 5));
-    if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
-    w >>= (base & 31);
-    if constexpr (RPW < 32) w &= (1u << RPW) - 1u;
-    if (w == 0u) continue;  // every row of this step is deleted / filtered out: read nothing
-
+  // Score the (up to) R rows this lane group holds -- row[r] valid iff on[r] -- and feed the warp list.
+  auto score_rows = [&](const int64_t (&row)[R], const bool (&on)[R]) {
     float acc[R];
-    bool on[R];
     const uint4* rp[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int local = r * G + gi;
-      on[r] = (w >> local) & 1u;
-      rp[r] = mat + (base + local) * row_chunks;
+      rp[r] = mat + row[r] * row_chunks;
       acc[r] = 0.f;
     }
     for (int c0 = 0; c0 < row_chunks; c0 += LPR * CH) {
@@ -193,9 +182,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int local = r * G + gi;
       const float sc = acc[r];
-      const uint64_t key = (on[r] && sc == sc) ? make_key(sc, static_cast<uint32_t>(base + local)) : 0ull;
+      const uint64_t key = (on[r] && sc == sc) ? make_key(sc, static_cast<uint32_t>(row[r])) : 0ull;
       unsigned m = __ballot_sync(0xffffffffu, sub == 0 && key > thr && key < upper);
       while (m) {
         const int srcl = __ffs(m) - 1;
@@ -204,6 +192,57 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
         if (x > thr) {
           L.insert(x, lane);
           thr = L.get(k - 1);
+        }
+      }
+    }
+  };
+
+  if constexpr (!SPARSE) {
+    // Dense walk: a warp step covers RPW consecutive rows (one bitmap word covers a step); steps are
+    // interleaved over all warps of the grid.  (Fetching the bitmap word one step ahead was measured
+    // on the B200 and lost: +15 % on the bf16 scan from the extra live registers.)
+    const int64_t n_steps = (p.n_rows + RPW - 1) / RPW;
+    for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; step < n_steps; step += total_warps) {
+      const int64_t base = step * RPW;
+      uint32_t w = __ldg(p.active + (base >> 5));
+      if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
+      w >>= (base & 31);
+      if constexpr (RPW < 32) w &= (1u << RPW) - 1u;
+      if (w == 0u) continue;  // every row of this step is deleted / filtered out: read nothing
+      int64_t row[R];
+      bool on[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int local = r * G + gi;
+        on[r] = (w >> local) & 1u;
+        row[r] = base + local;
+      }
+      score_rows(row, on);
+    }
+  } else {
+    // Sparse walk (selective prefilters): a warp takes one bitmap word = 32 consecutive rows at a
+    // time and packs only the SET bits into its RPW row slots, so filtered-out rows cost neither
+    // loop steps nor bitmap round trips (the dense walk pays one step per RPW rows regardless).
+    const int64_t n_words = (p.n_rows + 31) >> 5;
+    for (int64_t wi = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; wi < n_words; wi += total_warps) {
+      uint32_t w = __ldg(p.active + wi);
+      if (w != 0u && p.prefilter) w &= __ldg(p.prefilter + wi);
+      while (w != 0u) {
+        int64_t row[R];
+        bool on[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned bit = __fns(w, 0, r * G + gi + 1);  // position of this slot's set bit
+          on[r] = bit < 32u;
+          row[r] = (wi << 5) + (on[r] ? bit : 0u);
+        }
+        score_rows(row, on);
+        // drop the RPW lowest set bits that were just consumed
+        if constexpr (RPW >= 32) {
+          w = 0u;
+        } else {
+          const unsigned last = __fns(w, 0, RPW);
+          w = (last < 31u) ? (w & (0xffffffffu << (last + 1))) : 0u;
         }
       }
     }
@@ -285,7 +324,9 @@ template <bool BF16, int LPR, int CH>
 static int launch_scan_t(const ScanParams& p, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
                       static_cast<size_t>(kScanWarps) * p.k * sizeof(uint64_t);
-  auto kern = scan_topk_kernel<BF16, LPR, CH>;
+  // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
+  const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
+  auto kern = sparse ? scan_topk_kernel<BF16, LPR, CH, true> : scan_topk_kernel<BF16, LPR, CH, false>;
   if (smem > 48 * 1024) {
     PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
