@@ -882,7 +882,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       PVDB_TRY(run_pass(0, sample_tiles, nullptr, nullptr, carry, init_thr, true));
       PVDB_TRY(run_pass(sample_tiles, total_tiles - sample_tiles, init_thr, carry, nullptr, nullptr, false));
     } else {
-      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr, false));
+      // small problem, single pass: pinning each unit to one query tile (pair) keeps it to ONE cold
+      // start; the few surplus units that idle cost less than warming up several states per CTA
+      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr, true));
     }
   }
   return PVDB_OK;
