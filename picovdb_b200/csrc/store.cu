@@ -3,7 +3,10 @@
 //                                               picovdb/pico_vdb.py:58-68, 413-472)
 //   delete = clear active bit + zero row       (pico_vdb.py:514-531)
 //   row fetch / download / raw upload / compaction (pico_vdb.py:945, 356, 233-259, 840-848)
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -15,8 +18,103 @@ thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
 
 // ---------------------------------------------------------------------------- buffers
+// ---- CUDA virtual memory management entry points, resolved at run time (no link-time libcuda) ----
+namespace {
+struct VmmApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+
+template <typename F>
+bool resolve(const char* name, F& fn) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  fn = reinterpret_cast<F>(ptr);
+  return true;
+}
+
+VmmApi& vmm_api() {
+  static VmmApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (getenv("PVDB_NO_VMM") == nullptr) {
+      api.ok = resolve("cuMemAddressReserve", api.reserve) && resolve("cuMemAddressFree", api.addr_free) &&
+               resolve("cuMemCreate", api.create) && resolve("cuMemRelease", api.release) &&
+               resolve("cuMemMap", api.map) && resolve("cuMemUnmap", api.unmap) &&
+               resolve("cuMemSetAccess", api.set_access) &&
+               resolve("cuMemGetAllocationGranularity", api.granularity);
+      int dev = 0, supported = 0;
+      if (api.ok && cudaGetDevice(&dev) == cudaSuccess)
+        // CU_DEVICE_ATTRIBUTE_VIRTUAL_MEMORY_MANAGEMENT_SUPPORTED (102); the runtime enum has no name for it
+        cudaDeviceGetAttribute(&supported, static_cast<cudaDeviceAttr>(102), dev);
+      api.ok = api.ok && supported != 0;
+    }
+  }
+  return api;
+}
+
+constexpr size_t kVaReserve = 256ull << 30;  // address range per buffer; physical memory follows demand
+}  // namespace
+
 int DeviceBuffer::grow(size_t new_bytes, cudaStream_t stream) {
   if (new_bytes <= bytes) return PVDB_OK;
+  VmmApi& api = vmm_api();
+  if (api.ok && (ptr == nullptr || vmm)) {
+    int dev = 0;
+    PVDB_CUDA(cudaGetDevice(&dev));
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev;
+    size_t gran = 0;
+    if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0)
+      return fail(PVDB_ERR_CUDA, "cuMemGetAllocationGranularity failed");
+    if (ptr == nullptr) {
+      CUdeviceptr base = 0;
+      const size_t want = std::max(kVaReserve, (new_bytes + gran - 1) / gran * gran);
+      if (api.reserve(&base, want, 0, 0, 0) != CUDA_SUCCESS)
+        return fail(PVDB_ERR_OOM, "cuMemAddressReserve(%zu bytes) failed", want);
+      ptr = reinterpret_cast<void*>(base);
+      va_bytes = want;
+      vmm = true;
+    }
+    const size_t add = (new_bytes - bytes + gran - 1) / gran * gran;
+    if (bytes + add > va_bytes)
+      return fail(PVDB_ERR_OOM, "store buffer would exceed its reserved address range (%zu bytes)", va_bytes);
+    CUmemGenericAllocationHandle h = 0;
+    if (api.create(&h, add, &prop, 0) != CUDA_SUCCESS)
+      return fail(PVDB_ERR_OOM, "cuMemCreate(%zu bytes) failed: out of device memory", add);
+    const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(ptr) + bytes;
+    if (api.map(at, add, 0, h, 0) != CUDA_SUCCESS) {
+      api.release(h);
+      return fail(PVDB_ERR_CUDA, "cuMemMap failed");
+    }
+    CUmemAccessDesc acc{};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (api.set_access(at, add, &acc, 1) != CUDA_SUCCESS) {
+      api.unmap(at, add);
+      api.release(h);
+      return fail(PVDB_ERR_CUDA, "cuMemSetAccess failed");
+    }
+    chunks.push_back({static_cast<unsigned long long>(h), bytes, add});
+    PVDB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(at), 0, add, stream));
+    bytes += add;
+    return PVDB_OK;
+  }
+  // plain allocation (no VMM support): allocate, copy, free
   void* np = nullptr;
   PVDB_CUDA(cudaMalloc(&np, new_bytes));
   if (bytes) PVDB_CUDA(cudaMemcpyAsync(np, ptr, bytes, cudaMemcpyDeviceToDevice, stream));
@@ -29,7 +127,20 @@ int DeviceBuffer::grow(size_t new_bytes, cudaStream_t stream) {
 }
 
 void DeviceBuffer::release() {
-  if (ptr) cudaFree(ptr);
+  if (vmm) {
+    VmmApi& api = vmm_api();
+    cudaDeviceSynchronize();
+    for (const Chunk& c : chunks) {
+      api.unmap(reinterpret_cast<CUdeviceptr>(ptr) + c.offset, c.size);
+      api.release(static_cast<CUmemGenericAllocationHandle>(c.handle));
+    }
+    chunks.clear();
+    if (ptr) api.addr_free(reinterpret_cast<CUdeviceptr>(ptr), va_bytes);
+    vmm = false;
+    va_bytes = 0;
+  } else if (ptr) {
+    cudaFree(ptr);
+  }
   ptr = nullptr;
   bytes = 0;
 }
@@ -215,6 +326,8 @@ int pvdb_store::ensure_capacity(int64_t need_rows, cudaStream_t s) {
   if ((flags & PVDB_STORE_FIXED_CAPACITY) && capacity > 0)
     return fail(PVDB_ERR_CAPACITY, "Database capacity exceeded (%lld > %lld rows)",
                 static_cast<long long>(need_rows), static_cast<long long>(capacity));
+  // geometric growth keeps appends amortised O(1); with VMM-backed buffers a growth step only maps
+  // more memory (no copy), without it the step is a reallocate-and-copy
   int64_t cap = std::max<int64_t>(need_rows, capacity + capacity / 2);
   cap = (cap + 1023) & ~int64_t(1023);
   if (flags & PVDB_STORE_F32) PVDB_TRY(f32.grow(static_cast<size_t>(cap) * ld_f32 * sizeof(float), s));

@@ -3,15 +3,24 @@
 #pragma once
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
 namespace pvdb {
 
 // One growable device allocation.  Growth keeps the contents and zero-fills the new tail.
+// Backed by CUDA virtual memory management when the driver offers it: a large address range is
+// reserved once and physical memory is mapped behind it as the store grows, so growth never copies,
+// never needs 2x transient memory, and the base pointer (hence every TMA tensor map) stays valid.
+// (The reference re-allocates and copies the whole matrix on every append, pico_vdb.py:451-462.)
 struct DeviceBuffer {
   void* ptr = nullptr;
-  size_t bytes = 0;
+  size_t bytes = 0;      // usable (mapped) bytes
+  bool vmm = false;
+  size_t va_bytes = 0;   // reserved address range (vmm)
+  struct Chunk { unsigned long long handle; size_t offset, size; };
+  std::vector<Chunk> chunks;
   int grow(size_t new_bytes, cudaStream_t stream);  // no-op when new_bytes <= bytes
   void release();
 };
