@@ -55,7 +55,6 @@ constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
 constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom + 32 slots)
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
-constexpr int kDefaultQGroup = 32;  // see decode_visit
 constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
@@ -81,29 +80,12 @@ struct BatchParams {
                          // else a multiple of the query-tile(-pair) count: unit u keeps ONE query tile
                          // and units >= visit_stride stay idle (cheap cold start for the sample pass)
   const float* init_thr; // optional [nq]: a proven lower bound of each query's k_sel-th best score
-  int q_group;         // query tiles that share a database tile back to back (visit order)
 };
 
-// Visit order: query tiles are taken in groups of q_group; inside a group visits run tile-major
-// (database tile t, then the group's query tiles).  q_group = q_tiles is pure tile-major (every
-// database tile is fetched from HBM once, but q_tiles CTAs hit the same L2 lines at the same
-// instant); smaller groups trade HBM re-reads (q_tiles / q_group passes) for less L2 contention.
+// Visit numbering is tile-major: v = t * q_tiles + qt.
 __device__ __forceinline__ void decode_visit(const BatchParams& p, int64_t v, int& t, int& qt) {
-  const int g = p.q_group;
-  const int full_groups = p.q_tiles / g;
-  const int64_t per_group = static_cast<int64_t>(p.n_tiles) * g;
-  const int64_t full = per_group * full_groups;
-  if (v < full) {
-    const int qg = static_cast<int>(v / per_group);
-    const int64_t rem = v - qg * per_group;
-    t = static_cast<int>(rem / g);
-    qt = qg * g + static_cast<int>(rem - static_cast<int64_t>(t) * g);
-  } else {
-    const int r = p.q_tiles - full_groups * g;  // > 0 here
-    const int64_t rem = v - full;
-    t = static_cast<int>(rem / r);
-    qt = full_groups * g + static_cast<int>(rem - static_cast<int64_t>(t) * r);
-  }
+  t = static_cast<int>(v / p.q_tiles);
+  qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
 }
 
 // Cluster variant (CL = 2): the two CTAs of a cluster always work on the same database tile and on
@@ -822,7 +804,6 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     p.pool_cap = k_sel <= 32 ? 128 : 256;
     p.active = static_cast<const uint32_t*>(s->active.ptr);
     p.prefilter = d_pref;
-    p.q_group = p.q_tiles;  // pure tile-major visit numbering
 
     // Sample pass: the first 1/16 of the tiles is searched on its own; the k_sel-th best score it
     // finds for a query is a proven lower bound of that query's final k_sel-th best, so the main

@@ -57,7 +57,7 @@ class ShardedSearch:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._host_merge = merge
         local.set_row_base(self.row0)
-        self._bufs: dict[tuple[int, int], dict[str, torch.Tensor]] = {}
+        self._bufs: dict[tuple, dict[str, torch.Tensor]] = {}
 
     # ------------------------------------------------------------------ device path
     def _buffers(self, nq: int, k: int, device) -> dict[str, torch.Tensor]:
@@ -65,11 +65,15 @@ class ShardedSearch:
         b = self._bufs.get(key)
         if b is None:
             nbytes = packed_result_bytes(nq, k)
+            # merged result: one packed block {rows int64 | scores fp32} so the host path needs ONE copy
+            out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            n_out = nq * k
             b = {
                 "local": torch.empty(nbytes, dtype=torch.uint8, device=device),
                 "all": torch.empty(self.world * nbytes, dtype=torch.uint8, device=device),
-                "scores": torch.empty((nq, k), dtype=torch.float32, device=device),
-                "rows": torch.empty((nq, k), dtype=torch.int64, device=device),
+                "out": out,
+                "rows": out[: n_out * 8].view(torch.int64).view(nq, k),
+                "scores": out[n_out * 8 : n_out * 12].view(torch.float32).view(nq, k),
             }
             self._bufs[key] = b
         return b
@@ -110,14 +114,24 @@ class ShardedSearch:
         """numpy in / numpy out.  ``prefilter`` is this rank's slice of the row mask."""
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if self._host_merge is None and torch.cuda.is_available():
-            dq = torch.from_numpy(q).cuda(non_blocking=True)
+            nq = q.shape[0]
+            st = self._staging(nq, k, q.shape[1])
+            st["hq"].numpy()[...] = q                       # pinned staging -> async H2D
+            st["dq"].copy_(st["hq"], non_blocking=True)
             dp = None
             if prefilter is not None:
                 from .engine import pack_row_mask
 
                 dp = torch.from_numpy(pack_row_mask(prefilter).view(np.int32)).cuda(non_blocking=True)
-            s, r = self.search_dev(dq, k, precision=precision, d_prefilter=dp)
-            return s.cpu().numpy(), r.cpu().numpy()
+            self.search_dev(st["dq"], k, precision=precision, d_prefilter=dp)
+            b = self._buffers(nq, k, st["dq"].device)
+            st["hout"].copy_(b["out"], non_blocking=True)   # one packed D2H: rows then scores
+            torch.cuda.current_stream().synchronize()
+            raw = st["hout"].numpy()
+            n_out = nq * k
+            rows = raw[: n_out * 8].view("<i8").reshape(nq, k).copy()
+            scores = raw[n_out * 8 : n_out * 12].view("<f4").reshape(nq, k).copy()
+            return scores, rows
         # process group without GPUs (tests): same packing / gather / merge flow on host tensors
         if self._host_merge is None:
             raise RuntimeError("ShardedSearch needs CUDA (no CPU compute path)")
@@ -138,6 +152,20 @@ class ShardedSearch:
         rows = [blk[: n_out * 8].view("<i8").reshape(nq, k) for blk in blocks]
         scores = [blk[n_out * 8 : n_out * 12].view("<f4").reshape(nq, k) for blk in blocks]
         return self._host_merge(scores, rows, k)
+
+    def _staging(self, nq: int, k: int, dim: int) -> dict[str, torch.Tensor]:
+        """Pinned host + device staging buffers for the host-buffer path, cached per (nq, k)."""
+        key = ("staging", nq, k)
+        st = self._bufs.get(key)
+        if st is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            st = {
+                "hq": torch.empty((nq, dim), dtype=torch.float32).pin_memory(),
+                "dq": torch.empty((nq, dim), dtype=torch.float32, device=dev),
+                "hout": torch.empty(packed_result_bytes(nq, k), dtype=torch.uint8).pin_memory(),
+            }
+            self._bufs[key] = st
+        return st
 
     def _host_row_base(self) -> int:
         # a test engine that does not implement row_base itself gets the offset added here
