@@ -56,6 +56,7 @@ constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
 constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
+constexpr bool kPairDefault = false;  // flipped once the pair variant is validated on hardware
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
@@ -155,6 +156,46 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint32_t bar, uint16_t mask) {
                ::"r"(bar), "h"(mask)
                : "memory");
 }
+// ---- cta_group::2 (CTA pair) forms.  Shared-memory addresses of the two CTAs of a pair differ in
+// one bit of the shared::cluster window; clearing it addresses the even (leader) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -218,10 +259,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   return lo | (hi << 32);
 }
 // instruction descriptor: D=f32, A/B = tf32 (2) or bf16 (1), both K-major, N=256, M=128
-__host__ __device__ constexpr uint32_t make_idesc(bool bf16) {
+__host__ __device__ constexpr uint32_t make_idesc(bool bf16, int m = kBM) {
   const uint32_t fmt = bf16 ? 1u : 2u;
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) |
-         (static_cast<uint32_t>(kBM >> 4) << 24);
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------------------- warp bitonic sort
@@ -327,7 +368,12 @@ __device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float
 }
 
 // ---------------------------------------------------------------------------- the GEMM + top-k kernel
-template <bool BF16, int NI, int CL>
+// PAIR (implies CL == 2): the two CTAs of a cluster form one cta_group::2 MMA unit -- M = 256 (each
+// CTA's own 128-query tile), N = 256 with each CTA holding HALF of the database tile's rows.  A stage
+// is then 16 KB + 16 KB per CTA, so the same 192 KB ring holds 6 stages instead of 4 (deeper
+// pipeline against L2 latency) and each CTA pulls 32 KB instead of 48 KB per K block.  The leader
+// (even) CTA issues the MMAs and owns the full / tmem_empty barriers; commits are multicast.
+template <bool BF16, int NI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                   const BatchParams p) {
@@ -335,9 +381,14 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   // 1024-byte alignment is required by the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* stage_base = smem;
+  static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
+  constexpr int NS = PAIR ? 6 : kStages;                                        // ring stages
+  constexpr int kStageB = PAIR ? kStageBBytes / 2 : kStageBBytes;               // B bytes per stage in this CTA
+  constexpr int kStageAll = kStageABytes + kStageB;
+  static_assert(static_cast<size_t>(NS) * kStageAll == kRingBytes, "both layouts use the same ring");
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
   float* s_thr = reinterpret_cast<float*>(smem + kRingBytes + 256);                   // [q_tiles][128]
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_thr + kMaxQTiles * kBM);            // [q_tiles][128]
   uint8_t* s_touched = reinterpret_cast<uint8_t*>(s_cnt + kMaxQTiles * kBM);          // [q_tiles]
@@ -352,27 +403,37 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kStages + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kStages + 2 + a); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (NS + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * NS + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * NS + 2 + a); };
+  const bool is_leader = !PAIR || cta_rank == 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);  // every CTA that receives the multicast must release the slot
+      // multicast variant: every CTA that receives the multicast must release the slot;
+      // pair variant: one multicast commit from the leader's MMA thread releases it in both CTAs
+      mbar_init(empty_bar(s), PAIR ? 1 : CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tempty_bar(a), PAIR ? 8 : 4);  // one arrival per epilogue warp (of both CTAs for a pair)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x < kMaxQTiles) s_touched[threadIdx.x] = 0;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
@@ -396,9 +457,23 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         decode_unit_visit<CL>(p, v, cta_rank, t, qt);  // a padding query tile loads zeros (out of bounds)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+          const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint32_t b_dst = a_dst + kStageABytes;
-          mbar_expect_tx(full_bar(stage), kStageBytes);
+          if constexpr (PAIR) {
+            // both CTAs load their own query slice and their half of the tile's rows into their own
+            // shared memory; all bytes are counted on the LEADER's full barrier
+            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+            if (is_leader) mbar_expect_tx(full_bar(stage), 2 * kStageAll);
+            tma_load_2d_pair(a_dst, &map_q, lbar, kb * kElemsPerStage, qt * kBM);
+            tma_load_2d_pair(b_dst, &map_db, lbar, kb * kElemsPerStage,
+                             (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * (kBN / 2));
+            if (++stage == NS) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            continue;
+          }
+          mbar_expect_tx(full_bar(stage), kStageAll);
           tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
           if constexpr (CL == 1) {
             tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
@@ -408,7 +483,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             tma_load_2d_mc(b_dst + cta_rank * (kStageBBytes / CL), &map_db, full_bar(stage), kb * kElemsPerStage,
                            (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * kShareRows, kClusterMask);
           }
-          if (++stage == kStages) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1u;
           }
@@ -417,8 +492,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BF16);
+    if (lane == 0 && is_leader) {
+      constexpr uint32_t idesc = make_idesc(BF16, PAIR ? 2 * kBM : kBM);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -430,24 +505,31 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageBytes);
+          const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint64_t da = make_smem_desc(a_addr);
           const uint64_t db = make_smem_desc(a_addr + kStageABytes);
 #pragma unroll
           for (int j = 0; j < kKBytes / 32; ++j) {
             // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
-                       (kb | j) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              umma_pair<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                              (kb | j) != 0 ? 1u : 0u);
+            else
+              umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                         (kb | j) != 0 ? 1u : 0u);
           }
           // ring slot reusable once these MMAs retire (in every CTA the multicast writes to)
-          if constexpr (CL == 1) tcgen05_commit(empty_bar(stage));
+          if constexpr (PAIR) tcgen05_commit_pair(empty_bar(stage), kClusterMask);
+          else if constexpr (CL == 1) tcgen05_commit(empty_bar(stage));
           else tcgen05_commit_mc(empty_bar(stage), kClusterMask);
-          if (++stage == kStages) {
+          if (++stage == NS) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tcgen05_commit(tfull_bar(acc));  // accumulator complete
+        // accumulator complete (in both CTAs' tensor memory for a pair)
+        if constexpr (PAIR) tcgen05_commit_pair(tfull_bar(acc), kClusterMask);
+        else tcgen05_commit(tfull_bar(acc));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -480,7 +562,10 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         tcgen05_fence_after();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (is_leader) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);
+        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -548,7 +633,10 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (is_leader) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -581,7 +669,10 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -740,7 +831,7 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
   return PVDB_OK;
 }
 
-template <bool BF16, int CL>
+template <bool BF16, int CL, bool PAIR>
 static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p, int grid,
                           cudaStream_t st) {
   auto run = [&](auto kern) -> int {
@@ -762,8 +853,8 @@ static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const B
     return PVDB_OK;
   };
   switch (p.pool_cap) {
-    case 128: return run(batch_topk_kernel<BF16, 4, CL>);
-    default: return run(batch_topk_kernel<BF16, 8, CL>);
+    case 128: return run(batch_topk_kernel<BF16, 4, CL, PAIR>);
+    default: return run(batch_topk_kernel<BF16, 8, CL, PAIR>);
   }
 }
 
@@ -780,6 +871,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   // CTA fetches half of the tile's rows), which cuts the L2 -> shared-memory traffic per CTA from
   // 48 KB to 32 KB per K block.  A single query tile has nobody to share with.
   const bool cluster_ok = getenv("PVDB_BATCH_NO_CLUSTER") == nullptr;
+  // cta_group::2 MMAs (one M=256 instruction per CTA pair); PVDB_BATCH_PAIR=0 keeps the multicast variant
+  const char* pair_env = getenv("PVDB_BATCH_PAIR");
+  const bool pair_mma = pair_env ? atoi(pair_env) != 0 : kPairDefault;
   CUtensorMap mdb, mdb_half;
   if (use_bf16) {
     PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
@@ -845,12 +939,15 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       const int n_qp = (p.q_tiles + cl - 1) / cl, n_units = grid / cl;
       p.visit_stride = (pin_query_tiles && n_units >= n_qp) ? n_qp * (n_units / n_qp) : 0;
       PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
-      if (cluster) {
-        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2>(mq, mdb_half, p, grid, st)));
-        else PVDB_TRY((launch_batch_t<false, 2>(mq, mdb_half, p, grid, st)));
+      if (cluster && pair_mma) {
+        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2, true>(mq, mdb_half, p, grid, st)));
+        else PVDB_TRY((launch_batch_t<false, 2, true>(mq, mdb_half, p, grid, st)));
+      } else if (cluster) {
+        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2, false>(mq, mdb_half, p, grid, st)));
+        else PVDB_TRY((launch_batch_t<false, 2, false>(mq, mdb_half, p, grid, st)));
       } else {
-        if (use_bf16) PVDB_TRY((launch_batch_t<true, 1>(mq, mdb, p, grid, st)));
-        else PVDB_TRY((launch_batch_t<false, 1>(mq, mdb, p, grid, st)));
+        if (use_bf16) PVDB_TRY((launch_batch_t<true, 1, false>(mq, mdb, p, grid, st)));
+        else PVDB_TRY((launch_batch_t<false, 1, false>(mq, mdb, p, grid, st)));
       }
       finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
           p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
