@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--cpu-queries", type=int, default=24, help="single queries timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.warmup = max(3, args.warmup)  # timing hygiene: never fewer than 3 untimed warm-up steps
     if args.workload == "c5":
         args.rows = args.rows or 100_000_000
         args.dim = args.dim or 384
@@ -102,7 +103,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"],
+                 "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             threading.Thread(target=self._pump, daemon=True).start()
@@ -312,12 +313,13 @@ def run_b200(args, world, rank, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident inputs/outputs
+    # ---- value: device-resident inputs/outputs (clock sampling starts before the warm-up so that
+    # short timed regions still get samples taken under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = N.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()

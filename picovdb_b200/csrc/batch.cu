@@ -56,7 +56,10 @@ constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
 constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
 constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
-constexpr bool kPairDefault = false;  // flipped once the pair variant is validated on hardware
+// The pair (cta_group::2) variant is validated (all batch tests pass with PVDB_BATCH_PAIR=1) but measured
+// SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
+// C5 batch: 34.9 vs 32.4 ms), so it stays opt-in.
+constexpr bool kPairDefault = false;
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
