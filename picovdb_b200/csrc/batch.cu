@@ -268,6 +268,45 @@ __host__ __device__ constexpr uint32_t make_idesc(bool bf16, int m = kBM) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------------------- warp bitonic sort
+// 32*NI keys, element e = i*32 + lane, sorted descending.
+template <int NI>
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[NI], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 32 * NI; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int sj = stride >> 5;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          if ((i & sj) == 0) {
+            const int e = i * 32 + lane;
+            const bool desc = (e & size) == 0;
+            const uint64_t a = key[i], b = key[i | sj];
+            if ((a < b) == desc) {
+              key[i] = b;
+              key[i | sj] = a;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int e = i * 32 + lane;
+          const uint64_t other = shfl_xor_u64(key[i], stride);
+          const bool desc = (e & size) == 0;
+          const bool lower = (lane & stride) == 0;
+          const bool take_max = (desc == lower);
+          const uint64_t mx = key[i] > other ? key[i] : other;
+          const uint64_t mn = key[i] > other ? other : key[i];
+          key[i] = take_max ? mx : mn;
+        }
+      }
+    }
+  }
+}
+
 // Co-operative prune of one query's pool: keep the best k_sel keys (sorted, zero padded, at the
 // front).  Returns (through the references) the pool's new count and threshold.
 template <int NI>

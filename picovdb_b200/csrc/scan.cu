@@ -248,71 +248,12 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     }
   }
 
-  // ---- block merge and grid merge.
-  // Fast path (k <= 32): the k-th key of ANY list is a lower bound of the merged k-th key, so the
-  // lists are first filtered against the largest such bound; what survives (k plus a handful of
-  // keys) is compacted into shared memory and sorted by one warp in registers.  This replaces a
-  // serial insert-merge of 16 (block) / 296 (grid) lists by warp 0, which was ~35 % of the kernel's
-  // ~25 us fixed cost.  More than kCandCap survivors (tiny or adversarial inputs) or k > 32 take the
-  // general insert-merge path.
-  constexpr int kCandCap = 128;
-  __shared__ uint64_t s_bound[kScanWarps];
-  __shared__ uint64_t s_cand[kCandCap];
-  __shared__ int s_ncand;
-  const bool small_k = (k <= 32);
-
-  // compact this warp's qualifying keys (key >= bound, key != 0) into s_cand
-  auto offer = [&](uint64_t key, uint64_t bound) {
-    const bool q = key != 0ull && key >= bound;
-    const unsigned m = __ballot_sync(0xffffffffu, q);
-    if (m == 0u) return;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&s_ncand, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    const int pos = base + __popc(m & ((1u << lane) - 1u));
-    if (q && pos < kCandCap) s_cand[pos] = key;
-  };
-  // warp 0: sort the compacted candidates, return entry `lane` of the merged list (lane < k)
-  auto sorted_head = [&](int n) -> uint64_t {
-    uint64_t c[kCandCap / 32];
-#pragma unroll
-    for (int i = 0; i < kCandCap / 32; ++i) {
-      const int e = i * 32 + lane;
-      c[i] = (e < n) ? s_cand[e] : 0ull;
-    }
-    warp_sort_desc<kCandCap / 32>(c, lane);
-    return c[0];
-  };
-  auto warp_max_u64 = [&](uint64_t v) -> uint64_t {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint64_t other = shfl_xor_u64(v, o);
-      v = other > v ? other : v;
-    }
-    return v;
-  };
-
-  store_list(L, slist + warp * k, k, lane);  // needed by the general path only
-  if (lane == 0) s_bound[warp] = thr;        // this warp's k-th key (0 when it holds fewer than k)
-  if (tid == 0) s_ncand = 0;
+  // ---- block merge: warp 0 folds the other warps' lists into its own
+  store_list(L, slist + warp * k, k, lane);
   __syncthreads();
-  bool merged = false;
-  if (small_k) {
-    const uint64_t bound = warp_max_u64(lane < kScanWarps ? s_bound[lane] : 0ull);
-    offer(lane < k ? L.slot[0] : 0ull, bound);
-    __syncthreads();
-    const int n = s_ncand;
-    merged = (n <= kCandCap);
-    if (merged && warp == 0) {
-      const uint64_t head = sorted_head(n);
-      if (lane < k) p.partial[static_cast<size_t>(blockIdx.x) * k + lane] = head;
-    }
-  }
-  if (!merged && warp == 0) {
+  if (warp == 0) {
     for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
     store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
-  }
-  if (warp == 0) {
     __threadfence();
     __syncwarp();
     if (lane == 0) {
@@ -323,78 +264,58 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   __syncthreads();
   if (s_is_last == 0u) return;
 
-  // ---- last block: merge all per-block lists (sorted, zero padded, k keys each) and emit the result
+  // ---- last block: merge all per-block lists and emit the result
   __threadfence();
-  const int n_lists = static_cast<int>(gridDim.x);
-  uint64_t final_head = 0ull;  // warp 0: entry `lane` of the final list
-  bool done = false;
-  if (small_k) {
-    // bound = the largest k-th key over all block lists
-    uint64_t b = 0ull;
-    for (int i = tid; i < n_lists; i += kScanThreads) {
-      const uint64_t v = load_key<true>(p.partial + static_cast<size_t>(i) * k + (k - 1));
-      b = v > b ? v : b;
+  L.clear();
+  thr = 0ull;
+  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
+  // together so the L2 round trips overlap; a list whose whole head qualified continues through
+  // the general path.
+  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += kScanWarps * 8) {
+    uint64_t head[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * kScanWarps;
+      head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
+                    ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
+                    : 0ull;
     }
-    b = warp_max_u64(b);
-    if (lane == 0) s_bound[warp] = b;
-    if (tid == 0) s_ncand = 0;
-    __syncthreads();
-    const uint64_t bound = warp_max_u64(lane < kScanWarps ? s_bound[lane] : 0ull);
-    // every warp offers the heads of its share of the lists; eight lists are fetched together so
-    // the L2 round trips overlap
-    for (int b0 = warp; b0 < n_lists; b0 += kScanWarps * 8) {
-      uint64_t head[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int bi = b0 + j * kScanWarps;
-        head[j] = (bi < n_lists && lane < k) ? load_key<true>(p.partial + static_cast<size_t>(bi) * k + lane) : 0ull;
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) offer(head[j], bound);
-    }
-    __syncthreads();
-    const int n = s_ncand;
-    done = (n <= kCandCap);
-    if (done && warp == 0) final_head = sorted_head(n);
-  }
-  if (!done) {
-    // general path: every warp insert-merges every 16th block list, then warp 0 folds the 16 results
-    L.clear();
-    thr = 0ull;
-    for (int bi = warp; bi < n_lists; bi += kScanWarps)
-      merge_list<true>(L, thr, p.partial + static_cast<size_t>(bi) * k, k, k, lane);
-    __syncthreads();  // everyone is done reading slist from the block merge
-    store_list(L, slist + warp * k, k, lane);
-    __syncthreads();
-    if (warp == 0)
-      for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
-  }
-  if (warp == 0) {
-    if (done) {
-      if (lane < k) {
-        p.out_scores[lane] = final_head ? key_score(final_head) : -INFINITY;
-        p.out_rows[lane] = final_head ? p.row_base + static_cast<int64_t>(key_row(final_head)) : -1ll;
-      }
-      const uint64_t kth = shfl_u64(final_head, k - 1);
-      if (lane == 0) {
-        *p.next_upper = kth;
-        *p.ticket = 0u;
-      }
-    } else {
-#pragma unroll
-      for (int s2 = 0; s2 < kSlots; ++s2) {
-        const int e = s2 * 32 + lane;
-        if (e < k) {
-          const uint64_t key = L.slot[s2];
-          p.out_scores[e] = key ? key_score(key) : -INFINITY;
-          p.out_rows[e] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * kScanWarps;
+      if (b >= static_cast<int>(gridDim.x)) break;
+      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
+      const bool head_all = (m == 0xffffffffu);
+      while (m) {
+        const int srcl = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t x = shfl_u64(head[j], srcl);
+        if (x > thr) {
+          L.insert(x, lane);
+          thr = L.get(k - 1);
         }
       }
-      const uint64_t kth = L.get(k - 1);
-      if (lane == 0) {
-        *p.next_upper = kth;
-        *p.ticket = 0u;
+      if (head_all && k > 32) merge_list<true>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
+    }
+  }
+  __syncthreads();  // everyone is done reading slist from the first merge
+  store_list(L, slist + warp * k, k, lane);
+  __syncthreads();
+  if (warp == 0) {
+    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int e = s * 32 + lane;
+      if (e < k) {
+        const uint64_t key = L.slot[s];
+        p.out_scores[e] = key ? key_score(key) : -INFINITY;
+        p.out_rows[e] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
       }
+    }
+    const uint64_t kth = L.get(k - 1);
+    if (lane == 0) {
+      *p.next_upper = kth;
+      *p.ticket = 0u;
     }
   }
 }
