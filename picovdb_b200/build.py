@@ -1,9 +1,11 @@
 """In-tree build of the CUDA extension (sm_100a only).
 
-``python -m picovdb_b200.build`` compiles ``csrc/*.cu`` into ``picovdb_b200/libpicovdb_b200.so`` with
-nvcc.  The library links the CUDA runtime statically and resolves driver entry points at run
-time, so it loads (and its symbols can be inspected) on a machine without a GPU; every compute
-entry point fails with PVDB_ERR_CUDA there.
+``python -m picovdb_b200.build`` compiles every ``csrc/*.cu`` into an object file (in parallel, one
+nvcc process per translation unit, cached by a hash of the source + headers + flags under
+``picovdb_b200/_build/``) and links them into ``picovdb_b200/libpicovdb_b200.so``.  The library
+links the CUDA runtime statically and resolves driver entry points at run time, so it loads (and
+its symbols can be inspected) on a machine without a GPU; every compute entry point fails with
+PVDB_ERR_CUDA there.
 """
 from __future__ import annotations
 
@@ -12,35 +14,51 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
+OBJ_DIR = os.path.join(PKG_DIR, "_build")
 LIB_PATH = os.path.join(PKG_DIR, "libpicovdb_b200.so")
 STAMP_PATH = os.path.join(PKG_DIR, ".libpicovdb_b200.stamp")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 
-NVCC_FLAGS = [
+COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
-    "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 
 
 def _sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _fingerprint() -> str:
+def _headers_digest() -> bytes:
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + ["../../include/picovdb_b200.h"]
-    for f in files:
-        path = os.path.normpath(os.path.join(CSRC, f))
-        if os.path.isfile(path):
-            h.update(f.encode())
-            with open(path, "rb") as fh:
-                h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h", ".inl")):
+            with open(os.path.join(CSRC, f), "rb") as fh:
+                h.update(f.encode() + fh.read())
+    with open(os.path.join(INCLUDE, "picovdb_b200.h"), "rb") as fh:
+        h.update(fh.read())
+    h.update(" ".join(COMPILE_FLAGS).encode())
+    return h.digest()
+
+
+def _object_key(src: str, headers: bytes) -> str:
+    h = hashlib.sha256(headers)
+    with open(src, "rb") as fh:
+        h.update(fh.read())
+    return h.hexdigest()[:24]
+
+
+def _fingerprint() -> str:
+    headers = _headers_digest()
+    h = hashlib.sha256(" ".join(LINK_FLAGS).encode())
+    for src in _sources():
+        h.update(os.path.basename(src).encode() + _object_key(src, headers).encode())
     return h.hexdigest()
 
 
@@ -59,19 +77,43 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the shared library if the sources changed; return its path."""
+    """Compile what changed, link, return the library path."""
     if not force and is_current():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", LIB_PATH, *_sources()]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = _headers_digest()
+    jobs = []
+    objects = []
+    for src in _sources():
+        stem = os.path.splitext(os.path.basename(src))[0]
+        obj = os.path.join(OBJ_DIR, f"{stem}.{_object_key(src, headers)}.o")
+        objects.append(obj)
+        if force or not os.path.exists(obj):
+            jobs.append((src, obj))
+
+    def compile_one(job):
+        src, obj = job
+        cmd = [nvcc, *COMPILE_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-I", INCLUDE, "-c", src, "-o", obj + ".tmp"]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{res.stdout}\n{res.stderr}")
+        os.replace(obj + ".tmp", obj)
+        if verbose:
+            print(res.stderr, file=sys.stderr)
+
+    if jobs:
+        workers = max(1, min(len(jobs), os.cpu_count() or 1))
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(compile_one, jobs))
+    res = subprocess.run([nvcc, *LINK_FLAGS, "-o", LIB_PATH, *objects], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+        raise RuntimeError(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
+    keep = set(objects)
+    for f in os.listdir(OBJ_DIR):  # drop objects of older source versions
+        path = os.path.join(OBJ_DIR, f)
+        if path not in keep:
+            os.remove(path)
     with open(STAMP_PATH, "w") as f:
         f.write(_fingerprint())
     return LIB_PATH

@@ -17,333 +17,15 @@
 
 namespace pvdb {
 
-constexpr int kScanThreads = 512;
-constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanBlocksPerSM = 2;
-constexpr int kSlots = kFusedK / 32;
+int scan_grid_blocks() { return kNumSMs * 2; }
 
-int scan_grid_blocks() { return kNumSMs * kScanBlocksPerSM; }
-
-template <bool GLOBAL>
-__device__ __forceinline__ uint64_t load_key(const uint64_t* p) {
-  if constexpr (GLOBAL) {
-    return __ldcg(reinterpret_cast<const unsigned long long*>(p));  // L2: written by other SMs
-  } else {
-    return *p;
-  }
-}
-
-template <bool GLOBAL>
-__device__ __forceinline__ void merge_list(WarpList<kSlots>& L, uint64_t& thr, const uint64_t* src, int n, int k,
-                                           int lane) {
-  // src: descending list of n keys; k: rank whose key is the admission threshold
-  for (int base = 0; base < n; base += 32) {
-    const int e = base + lane;
-    const uint64_t v = (e < n) ? load_key<GLOBAL>(src + e) : 0ull;
-    unsigned m = __ballot_sync(0xffffffffu, v > thr);
-    if (m == 0) break;  // lists are descending: nothing further can qualify
-    while (m) {
-      const int srcl = __ffs(m) - 1;
-      m &= m - 1;
-      const uint64_t x = shfl_u64(v, srcl);
-      if (x > thr) {
-        L.insert(x, lane);
-        thr = L.get(k - 1);
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void store_list(const WarpList<kSlots>& L, uint64_t* dst, int k, int lane) {
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    const int e = s * 32 + lane;
-    if (e < k) dst[e] = L.slot[s];
-  }
-}
-
-__device__ __forceinline__ float dot_chunk_f32(const uint4& v, const float4& q, float acc) {
-  acc = fmaf(__uint_as_float(v.x), q.x, acc);
-  acc = fmaf(__uint_as_float(v.y), q.y, acc);
-  acc = fmaf(__uint_as_float(v.z), q.z, acc);
-  acc = fmaf(__uint_as_float(v.w), q.w, acc);
-  return acc;
-}
-// 8 bf16 values (one 16-byte chunk) against 8 fp32 query values; bf16 -> fp32 is a 16-bit shift
-__device__ __forceinline__ float dot_chunk_bf16(const uint4& v, const float4& q0, const float4& q1, float acc) {
-  acc = fmaf(__uint_as_float(v.x << 16), q0.x, acc);
-  acc = fmaf(__uint_as_float(v.x & 0xffff0000u), q0.y, acc);
-  acc = fmaf(__uint_as_float(v.y << 16), q0.z, acc);
-  acc = fmaf(__uint_as_float(v.y & 0xffff0000u), q0.w, acc);
-  acc = fmaf(__uint_as_float(v.z << 16), q1.x, acc);
-  acc = fmaf(__uint_as_float(v.z & 0xffff0000u), q1.y, acc);
-  acc = fmaf(__uint_as_float(v.w << 16), q1.z, acc);
-  acc = fmaf(__uint_as_float(v.w & 0xffff0000u), q1.w, acc);
-  return acc;
-}
-
-// LPR lanes cooperate on one row; each lane keeps CH 16-byte loads of R rows in flight
-// (CH * R == 8 -> eight independent 128-bit loads per lane per step).
-template <bool BF16, int LPR, int CH, bool SPARSE>
-__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kernel(const ScanParams p) {
-  constexpr int G = 32 / LPR;  // row groups per warp
-  constexpr int R = 8 / CH;    // rows in flight per group
-  constexpr int RPW = G * R;   // rows per warp step: a power of two <= 32, so one bitmap word covers it
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sq = reinterpret_cast<float*>(smem_raw);
-  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
-  __shared__ unsigned s_is_last;
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
-  const int sub = lane % LPR;
-  const int gi = lane / LPR;
-  const int k = p.k;
-
-  if (p.raw_query != nullptr) {
-    // Fused query preparation (picovdb/pico_vdb.py:584-591): every block normalises the raw query
-    // itself -- fp32 sum of squares, fp32 norm, IEEE division, zero query -> e0 -- which saves a
-    // kernel launch and a round trip through HBM on the single-query path.
-    __shared__ float s_part[kScanWarps];
-    float ss = 0.f;
-    for (int i = tid; i < p.query_floats; i += kScanThreads) {
-      const float x = (i < p.dim) ? p.raw_query[i] : 0.f;
-      sq[i] = x;
-      ss = fmaf(x, x, ss);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) s_part[warp] = ss;
-    __syncthreads();
-    double tot = 0.0;
-#pragma unroll
-    for (int w2 = 0; w2 < kScanWarps; ++w2) tot += static_cast<double>(s_part[w2]);
-    const float nrm = static_cast<float>(sqrt(tot));
-    for (int i = tid; i < p.query_floats; i += kScanThreads) {
-      const float x = sq[i];
-      sq[i] = (nrm == 0.f) ? (i == 0 ? 1.f : 0.f) : __fdiv_rn(x, nrm);
-    }
-  } else {
-    for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = p.query[i];
-  }
-  __syncthreads();
-  const float4* sq4 = reinterpret_cast<const float4*>(sq);
-
-  const uint64_t upper = p.upper ? *p.upper : ~0ull;
-  WarpList<kSlots> L;
-  L.clear();
-  uint64_t thr = 0ull;
-
-  const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanWarps;
-  const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
-  const int row_chunks = p.row_chunks;
-
-  // Score the (up to) R rows this lane group holds -- row[r] valid iff on[r] -- and feed the warp list.
-  auto score_rows = [&](const int64_t (&row)[R], const bool (&on)[R]) {
-    float acc[R];
-    const uint4* rp[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      rp[r] = mat + row[r] * row_chunks;
-      acc[r] = 0.f;
-    }
-    for (int c0 = 0; c0 < row_chunks; c0 += LPR * CH) {
-      uint4 v[R][CH];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int idx = c0 + i * LPR + sub;
-          v[r][i] = (on[r] && idx < row_chunks) ? ldg_stream(rp[r] + idx) : make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int idx = c0 + i * LPR + sub;
-        if (idx < row_chunks) {
-          if constexpr (BF16) {
-            const float4 q0 = sq4[2 * idx];
-            const float4 q1 = sq4[2 * idx + 1];
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = dot_chunk_bf16(v[r][i], q0, q1, acc[r]);
-          } else {
-            const float4 q = sq4[idx];
-#pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] = dot_chunk_f32(v[r][i], q, acc[r]);
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float sc = acc[r];
-      const uint64_t key = (on[r] && sc == sc) ? make_key(sc, static_cast<uint32_t>(row[r])) : 0ull;
-      unsigned m = __ballot_sync(0xffffffffu, sub == 0 && key > thr && key < upper);
-      while (m) {
-        const int srcl = __ffs(m) - 1;
-        m &= m - 1;
-        const uint64_t x = shfl_u64(key, srcl);
-        if (x > thr) {
-          L.insert(x, lane);
-          thr = L.get(k - 1);
-        }
-      }
-    }
-  };
-
-  if constexpr (!SPARSE) {
-    // Dense walk: a warp step covers RPW consecutive rows (one bitmap word covers a step); steps are
-    // interleaved over all warps of the grid.  (Fetching the bitmap word one step ahead was measured
-    // on the B200 and lost: +15 % on the bf16 scan from the extra live registers.)
-    const int64_t n_steps = (p.n_rows + RPW - 1) / RPW;
-    for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; step < n_steps; step += total_warps) {
-      const int64_t base = step * RPW;
-      uint32_t w = __ldg(p.active + (base >> 5));
-      if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
-      w >>= (base & 31);
-      if constexpr (RPW < 32) w &= (1u << RPW) - 1u;
-      if (w == 0u) continue;  // every row of this step is deleted / filtered out: read nothing
-      int64_t row[R];
-      bool on[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int local = r * G + gi;
-        on[r] = (w >> local) & 1u;
-        row[r] = base + local;
-      }
-      score_rows(row, on);
-    }
-  } else {
-    // Sparse walk (selective prefilters): a warp takes one bitmap word = 32 consecutive rows at a
-    // time and packs only the SET bits into its RPW row slots, so filtered-out rows cost neither
-    // loop steps nor bitmap round trips (the dense walk pays one step per RPW rows regardless).
-    const int64_t n_words = (p.n_rows + 31) >> 5;
-    for (int64_t wi = static_cast<int64_t>(blockIdx.x) * kScanWarps + warp; wi < n_words; wi += total_warps) {
-      uint32_t w = __ldg(p.active + wi);
-      if (w != 0u && p.prefilter) w &= __ldg(p.prefilter + wi);
-      while (w != 0u) {
-        int64_t row[R];
-        bool on[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const unsigned bit = __fns(w, 0, r * G + gi + 1);  // position of this slot's set bit
-          on[r] = bit < 32u;
-          row[r] = (wi << 5) + (on[r] ? bit : 0u);
-        }
-        score_rows(row, on);
-        // drop the RPW lowest set bits that were just consumed
-        if constexpr (RPW >= 32) {
-          w = 0u;
-        } else {
-          const unsigned last = __fns(w, 0, RPW);
-          w = (last < 31u) ? (w & (0xffffffffu << (last + 1))) : 0u;
-        }
-      }
-    }
-  }
-
-  // ---- block merge: warp 0 folds the other warps' lists into its own
-  store_list(L, slist + warp * k, k, lane);
-  __syncthreads();
-  if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
-    store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) {
-      const unsigned t = atomicAdd(p.ticket, 1u);
-      s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
-    }
-  }
-  __syncthreads();
-  if (s_is_last == 0u) return;
-
-  // ---- last block: merge all per-block lists and emit the result
-  __threadfence();
-  L.clear();
-  thr = 0ull;
-  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
-  // together so the L2 round trips overlap; a list whose whole head qualified continues through
-  // the general path.
-  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += kScanWarps * 8) {
-    uint64_t head[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = b0 + j * kScanWarps;
-      head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
-                    ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
-                    : 0ull;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = b0 + j * kScanWarps;
-      if (b >= static_cast<int>(gridDim.x)) break;
-      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
-      const bool head_all = (m == 0xffffffffu);
-      while (m) {
-        const int srcl = __ffs(m) - 1;
-        m &= m - 1;
-        const uint64_t x = shfl_u64(head[j], srcl);
-        if (x > thr) {
-          L.insert(x, lane);
-          thr = L.get(k - 1);
-        }
-      }
-      if (head_all && k > 32) merge_list<true>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
-    }
-  }
-  __syncthreads();  // everyone is done reading slist from the first merge
-  store_list(L, slist + warp * k, k, lane);
-  __syncthreads();
-  if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false>(L, thr, slist + w2 * k, k, k, lane);
-#pragma unroll
-    for (int s = 0; s < kSlots; ++s) {
-      const int e = s * 32 + lane;
-      if (e < k) {
-        const uint64_t key = L.slot[s];
-        p.out_scores[e] = key ? key_score(key) : -INFINITY;
-        p.out_rows[e] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
-      }
-    }
-    const uint64_t kth = L.get(k - 1);
-    if (lane == 0) {
-      *p.next_upper = kth;
-      *p.ticket = 0u;
-    }
-  }
-}
-
-template <bool BF16, int LPR, int CH>
-static int launch_scan_t(const ScanParams& p, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
-                      static_cast<size_t>(kScanWarps) * p.k * sizeof(uint64_t);
-  // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
-  const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
-  auto kern = sparse ? scan_topk_kernel<BF16, LPR, CH, true> : scan_topk_kernel<BF16, LPR, CH, false>;
-  if (smem > 48 * 1024) {
-    PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  }
-  kern<<<scan_grid_blocks(), kScanThreads, smem, stream>>>(p);
-  PVDB_LAUNCH_CHECK();
-  return PVDB_OK;
-}
-
-template <bool BF16, int LPR>
-static int launch_scan_ch(const ScanParams& p, int ch, cudaStream_t stream) {
-  switch (ch) {
-    case 1: return launch_scan_t<BF16, LPR, 1>(p, stream);
-    case 2: return launch_scan_t<BF16, LPR, 2>(p, stream);
-    case 4: return launch_scan_t<BF16, LPR, 4>(p, stream);
-    default: return launch_scan_t<BF16, LPR, 8>(p, stream);
-  }
-}
+// defined in scan_inst_*.cu
+template <bool BF16, bool SPARSE>
+int launch_scan_variant(const ScanParams& p, int lpr, int ch, cudaStream_t stream);
+extern template int launch_scan_variant<false, false>(const ScanParams&, int, int, cudaStream_t);
+extern template int launch_scan_variant<false, true>(const ScanParams&, int, int, cudaStream_t);
+extern template int launch_scan_variant<true, false>(const ScanParams&, int, int, cudaStream_t);
+extern template int launch_scan_variant<true, true>(const ScanParams&, int, int, cudaStream_t);
 
 int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   if (p.k < 1 || p.k > kFusedK) return fail(PVDB_ERR_INVALID, "scan: k=%d outside [1, %d]", p.k, kFusedK);
@@ -359,14 +41,12 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   else if (rc >= 16) lpr = 16;
   const int per_lane = (rc + lpr - 1) / lpr;
   const int ch = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
-  if (is_bf16) {
-    if (lpr == 32) return launch_scan_ch<true, 32>(p, ch, stream);
-    if (lpr == 16) return launch_scan_ch<true, 16>(p, ch, stream);
-    return launch_scan_ch<true, 8>(p, ch, stream);
-  }
-  if (lpr == 32) return launch_scan_ch<false, 32>(p, ch, stream);
-  if (lpr == 16) return launch_scan_ch<false, 16>(p, ch, stream);
-  return launch_scan_ch<false, 8>(p, ch, stream);
+  // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
+  const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
+  if (is_bf16) return sparse ? launch_scan_variant<true, true>(p, lpr, ch, stream)
+                             : launch_scan_variant<true, false>(p, lpr, ch, stream);
+  return sparse ? launch_scan_variant<false, true>(p, lpr, ch, stream)
+                : launch_scan_variant<false, false>(p, lpr, ch, stream);
 }
 
 // ---------------------------------------------------------------------------- query preparation

@@ -1,0 +1,6 @@
+// Scan kernel instantiations: bf16, dense walk (see scan_kernel.cuh).
+#include "scan_kernel.cuh"
+
+namespace pvdb {
+template int launch_scan_variant<true, false>(const ScanParams&, int, int, cudaStream_t);
+}  // namespace pvdb
