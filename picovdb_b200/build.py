@@ -27,6 +27,7 @@ COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    *os.environ.get("PVDB_NVCC_EXTRA", "").split(),  # e.g. -DPVDB_SCAN_THREADS=384 for tuning experiments
 ]
 LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static"]
 

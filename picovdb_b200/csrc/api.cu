@@ -158,10 +158,14 @@ extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, in
     PVDB_CUDA(cudaMemcpyAsync(s->d_prefilter.ptr, prefilter_bits, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     d_pref = static_cast<const uint32_t*>(s->d_prefilter.ptr);
   }
-  int64_t* d_rows = static_cast<int64_t*>(s->d_out.ptr);
+  // Small result sets are written by the kernels straight into the pinned host buffer (pinned
+  // memory is device-addressable under UVA), which removes the D2H copy from the latency of a
+  // single query; large ones go through HBM and one bulk copy.
+  const bool zero_copy = out_bytes <= (64u << 10);
+  int64_t* d_rows = static_cast<int64_t*>(zero_copy ? s->h_pinned.ptr : s->d_out.ptr);
   float* d_scores = reinterpret_cast<float*>(d_rows + n_out);
   PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_pref, flags, d_scores, d_rows, st));
-  PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (!zero_copy) PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
   PVDB_CUDA(cudaStreamSynchronize(st));
   const int64_t* h_rows = static_cast<const int64_t*>(s->h_pinned.ptr);
   std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));

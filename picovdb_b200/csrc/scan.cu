@@ -17,7 +17,7 @@
 
 namespace pvdb {
 
-int scan_grid_blocks() { return kNumSMs * 2; }
+int scan_grid_blocks() { return kNumSMs * kScanBlocksPerSM; }
 
 // defined in scan_inst_*.cu
 template <bool BF16, bool SPARSE>

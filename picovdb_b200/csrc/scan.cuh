@@ -6,6 +6,17 @@
 
 namespace pvdb {
 
+// launch shape of the scan kernel (tunable at build time for experiments)
+#ifndef PVDB_SCAN_THREADS
+#define PVDB_SCAN_THREADS 512
+#endif
+#ifndef PVDB_SCAN_BLOCKS_PER_SM
+#define PVDB_SCAN_BLOCKS_PER_SM 2
+#endif
+constexpr int kScanThreads = PVDB_SCAN_THREADS;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanBlocksPerSM = PVDB_SCAN_BLOCKS_PER_SM;
+
 struct ScanParams {
   const void* matrix;        // fp32 or bf16 row-major matrix
   int64_t n_rows;            // rows to scan (high-water mark)

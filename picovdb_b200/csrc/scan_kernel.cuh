@@ -8,9 +8,6 @@
 
 namespace pvdb {
 
-constexpr int kScanThreads = 512;
-constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanBlocksPerSM = 2;
 
 
 template <bool GLOBAL>
