@@ -118,6 +118,23 @@ int pvdb_store_active_bits(pvdb_store_t* s, uint32_t* out_words);
  * (replaces the fancy-index copy of vacuum(), pico_vdb.py:840-848). */
 int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int64_t n);
 
+/* ---- metadata columns: on-device evaluation of the dict `where` prefilters ---------------- */
+/* The reference evaluates {key: value} / {key: {"$in": [...]}} filters with a Python loop over the
+ * candidate docs on every query (pico_vdb.py:615-638).  Here the host dictionary-encodes a metadata
+ * key once (value -> int32 code >= 0, -1 = absent) and keeps the codes in a device column; a filter
+ * is then one kernel that turns (column, wanted codes) into the prefilter bitmap on the device.
+ * Write codes for rows[i] (rows == NULL: the n consecutive rows from row0).  Columns are numbered
+ * 0..15; rows never written read as "absent"; compaction drops all columns (re-upload them). */
+int pvdb_store_column_write(pvdb_store_t* s, int column, const int64_t* rows, int64_t row0,
+                            const int32_t* codes, int64_t n);
+int pvdb_store_column_drop(pvdb_store_t* s, int column);
+/* pvdb_search with the prefilter "column value in wanted[0..n_wanted)", optionally ANDed with a host
+ * bitmap (extra_bits, e.g. an `ids=` restriction).  *out_candidates receives the number of rows that
+ * were eligible (active, matching, in extra_bits) -- the reference's len(candidate_idx). */
+int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t nq, int k, int column,
+                      const int32_t* wanted, int n_wanted, const uint32_t* extra_bits, int flags,
+                      float* out_scores, int64_t* out_rows, int64_t* out_candidates);
+
 /* ---- search: replaces pico_vdb.py:584-591 + :683-714 -------------------------------------- */
 /* For each of nq queries (nq x dim fp32): normalise (zero -> e0) unless flagged, score every row
  * whose active bit -- and prefilter bit, when prefilter_bits != NULL (ceil(rows/32) words) -- is

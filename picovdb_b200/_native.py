@@ -80,6 +80,10 @@ SIGNATURES = {
     "pvdb_store_active_bits": (C.c_int, [_P, _P]),
     "pvdb_store_compact": (C.c_int, [_P, _P, _I64]),
     "pvdb_search": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P]),
+    "pvdb_search_where": (C.c_int, [_P, _P, _I64, C.c_int, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P,
+                                    C.POINTER(_I64)]),
+    "pvdb_store_column_write": (C.c_int, [_P, C.c_int, _P, _I64, _P, _I64]),
+    "pvdb_store_column_drop": (C.c_int, [_P, C.c_int]),
     "pvdb_search_dev": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P, _P]),
     "pvdb_merge_topk_dev": (C.c_int, [C.c_int, _P, _P, C.c_int, _I64, C.c_int, _I64, _I64, _P, _P, _P]),
     "pvdb_kernel_launches": (_I64, []),

@@ -173,6 +173,47 @@ extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, in
   return PVDB_OK;
 }
 
+extern "C" int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t nq, int k, int column,
+                                 const int32_t* wanted, int n_wanted, const uint32_t* extra_bits, int flags,
+                                 float* out_scores, int64_t* out_rows, int64_t* out_candidates) {
+  PVDB_ENTER(s);
+  if (nq < 0 || k < 1 || (nq > 0 && (!queries || !out_scores || !out_rows)))
+    return fail(PVDB_ERR_INVALID, "search_where: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
+  if (out_candidates) *out_candidates = 0;
+  if (nq == 0) return PVDB_OK;
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  const size_t q_bytes = static_cast<size_t>(nq) * s->dim * sizeof(float);
+  const size_t n_out = static_cast<size_t>(nq) * k;
+  const size_t out_bytes = n_out * (sizeof(int64_t) + sizeof(float));
+  PVDB_TRY(s->d_in.ensure(q_bytes));
+  PVDB_TRY(s->d_out.ensure(out_bytes));
+  PVDB_TRY(s->h_pinned.ensure(out_bytes + 16));
+  PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, queries, q_bytes, cudaMemcpyHostToDevice, st));
+  const bool zero_copy = out_bytes <= (64u << 10);
+  int64_t* d_rows = static_cast<int64_t*>(zero_copy ? s->h_pinned.ptr : s->d_out.ptr);
+  float* d_scores = reinterpret_cast<float*>(d_rows + n_out);
+  unsigned long long* h_count = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(s->h_pinned.ptr) +
+                                                                     ((out_bytes + 7) & ~size_t(7)));
+  *h_count = 0;
+  if (s->rows == 0) {
+    PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, nullptr, flags, d_scores, d_rows, st));
+  } else {
+    const uint32_t* d_bits = nullptr;
+    unsigned long long* d_count = nullptr;
+    PVDB_TRY(build_column_filter(s, column, wanted, n_wanted, extra_bits, &d_bits, &d_count, st));
+    PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_bits, flags, d_scores, d_rows, st));
+    PVDB_CUDA(cudaMemcpyAsync(h_count, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  }
+  if (!zero_copy) PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  const int64_t* h_rows = static_cast<const int64_t*>(s->h_pinned.ptr);
+  std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
+  std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
+  if (out_candidates) *out_candidates = static_cast<int64_t>(*h_count);
+  return PVDB_OK;
+}
+
 extern "C" int pvdb_merge_topk_dev(int device, const float* d_scores, const int64_t* d_rows, int nlists,
                                    int64_t nq, int k, int64_t scores_stride, int64_t rows_stride,
                                    float* d_out_scores, int64_t* d_out_rows, void* stream) {

@@ -334,6 +334,8 @@ int pvdb_store::ensure_capacity(int64_t need_rows, cudaStream_t s) {
   if (flags & PVDB_STORE_BF16)
     PVDB_TRY(bf16.grow(static_cast<size_t>(cap) * ld_bf16 * sizeof(__nv_bfloat16), s));
   PVDB_TRY(active.grow(static_cast<size_t>(cap / 32) * sizeof(uint32_t), s));
+  for (DeviceBuffer& col : column)
+    if (col.ptr) PVDB_TRY(col.grow(static_cast<size_t>(cap) * sizeof(uint32_t), s));
   capacity = cap;
   return PVDB_OK;
 }
@@ -409,6 +411,7 @@ extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
   s->f32.release();
   s->bf16.release();
   s->active.release();
+  s->drop_columns();
   for (Scratch* sc : {&s->d_in, &s->d_rows, &s->d_prefilter, &s->d_qn, &s->d_qn16, &s->d_partial, &s->d_out,
                       &s->d_misc, &s->h_pinned})
     sc->release();
@@ -723,6 +726,143 @@ extern "C" int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int
   std::swap(s->bf16, nb16);
   nf32.release();
   nb16.release();
+  s->drop_columns();  // row numbers changed: the host re-uploads the columns it still needs
   s->rows = n;
   return PVDB_OK;
 }
+
+// ---------------------------------------------------------------------------- metadata columns
+namespace pvdb {
+// column[row] = code + 1 (0 = absent)
+__global__ void column_write_kernel(uint32_t* __restrict__ col, const int64_t* __restrict__ rows, int64_t row0,
+                                    const int32_t* __restrict__ codes, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = rows ? rows[i] : row0 + i;
+    col[row] = static_cast<uint32_t>(codes[i] + 1);
+  }
+}
+
+// bits[w] = { row r in word w : active(r) && column[r] - 1 in wanted[] } (& extra[w]); also counts them.
+// One thread per row, one ballot per 32 rows.  `wanted` (sorted ascending) is searched linearly when
+// short, by bisection otherwise.
+__global__ void __launch_bounds__(256) column_filter_kernel(const uint32_t* __restrict__ col,
+                                                            const uint32_t* __restrict__ active,
+                                                            const uint32_t* __restrict__ extra, int64_t n_rows,
+                                                            const int32_t* __restrict__ wanted, int n_wanted,
+                                                            uint32_t* __restrict__ bits,
+                                                            unsigned long long* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_words = (n_rows + 31) >> 5;
+  unsigned long long local = 0;
+  for (int64_t w = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5; w < n_words;
+       w += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) {
+    uint32_t aw = __ldg(active + w);
+    if (extra) aw &= __ldg(extra + w);
+    bool hit = false;
+    const int64_t row = (w << 5) + lane;
+    if (((aw >> lane) & 1u) && row < n_rows) {
+      const int32_t code = static_cast<int32_t>(__ldg(col + row)) - 1;
+      if (code >= 0) {
+        if (n_wanted <= 8) {
+          for (int j = 0; j < n_wanted; ++j) hit |= (wanted[j] == code);
+        } else {
+          int lo = 0, hi = n_wanted - 1;
+          while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int32_t v = wanted[mid];
+            if (v == code) { hit = true; break; }
+            if (v < code) lo = mid + 1; else hi = mid - 1;
+          }
+        }
+      }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) {
+      bits[w] = word;
+      local += __popc(word);
+    }
+  }
+  if (lane == 0 && local) atomicAdd(count, local);
+}
+}  // namespace pvdb
+
+void pvdb_store::drop_columns() {
+  for (DeviceBuffer& col : column) col.release();
+}
+
+extern "C" int pvdb_store_column_write(pvdb_store_t* s, int column, const int64_t* rows, int64_t row0,
+                                       const int32_t* codes, int64_t n) {
+  PVDB_ENTER(s);
+  if (column < 0 || column >= pvdb_store::kMaxColumns) return fail(PVDB_ERR_INVALID, "column %d out of range", column);
+  if (n == 0) return PVDB_OK;
+  if (!codes || n < 0 || row0 < 0) return fail(PVDB_ERR_INVALID, "column_write: bad arguments");
+  if (rows) {
+    for (int64_t i = 0; i < n; ++i)
+      if (rows[i] < 0 || rows[i] >= s->rows)
+        return fail(PVDB_ERR_INVALID, "column_write: row %lld outside [0, %lld)", (long long)rows[i], (long long)s->rows);
+  } else if (row0 + n > s->rows) {
+    return fail(PVDB_ERR_INVALID, "column_write: range [%lld, %lld) outside the store", (long long)row0, (long long)(row0 + n));
+  }
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->column[column].grow(static_cast<size_t>(s->capacity) * sizeof(uint32_t), st));
+  PVDB_TRY(s->d_in.ensure(static_cast<size_t>(n) * sizeof(int32_t)));
+  PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, codes, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const int64_t* d_rows = nullptr;
+  if (rows) {
+    PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(n) * sizeof(int64_t)));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, rows, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    d_rows = static_cast<const int64_t*>(s->d_rows.ptr);
+  }
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, kNumSMs * 8)));
+  column_write_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(s->column[column].ptr), d_rows, row0,
+                                              static_cast<const int32_t*>(s->d_in.ptr), n);
+  PVDB_LAUNCH_CHECK();
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_column_drop(pvdb_store_t* s, int column) {
+  PVDB_ENTER(s);
+  if (column < 0 || column >= pvdb_store::kMaxColumns) return fail(PVDB_ERR_INVALID, "column %d out of range", column);
+  PVDB_CUDA(cudaStreamSynchronize(s->stream));
+  s->column[column].release();
+  return PVDB_OK;
+}
+
+namespace pvdb {
+// Build the prefilter bitmap for (column in wanted) on the device; returns the device bitmap and
+// leaves the eligible-row count in *d_count (device).  Used by pvdb_search_where (api.cu).
+int build_column_filter(pvdb_store* s, int column, const int32_t* wanted, int n_wanted, const uint32_t* extra_bits,
+                        const uint32_t** d_bits_out, unsigned long long** d_count_out, cudaStream_t st) {
+  if (column < 0 || column >= pvdb_store::kMaxColumns || s->column[column].ptr == nullptr)
+    return fail(PVDB_ERR_INVALID, "search_where: column %d has not been written", column);
+  if (n_wanted < 0 || (n_wanted > 0 && !wanted)) return fail(PVDB_ERR_INVALID, "search_where: bad wanted list");
+  const size_t n_words = static_cast<size_t>((s->rows + 31) >> 5);
+  // scratch layout: [bitmap][extra bitmap][wanted codes][count]
+  const size_t bm = (n_words * sizeof(uint32_t) + 255) & ~size_t(255);
+  const size_t wb = (static_cast<size_t>(n_wanted) * sizeof(int32_t) + 255) & ~size_t(255);
+  PVDB_TRY(s->d_prefilter.ensure(2 * bm + wb + 256));
+  unsigned char* base = static_cast<unsigned char*>(s->d_prefilter.ptr);
+  uint32_t* d_bits = reinterpret_cast<uint32_t*>(base);
+  uint32_t* d_extra = nullptr;
+  int32_t* d_wanted = reinterpret_cast<int32_t*>(base + 2 * bm);
+  unsigned long long* d_count = reinterpret_cast<unsigned long long*>(base + 2 * bm + wb);
+  if (extra_bits) {
+    d_extra = reinterpret_cast<uint32_t*>(base + bm);
+    PVDB_CUDA(cudaMemcpyAsync(d_extra, extra_bits, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  }
+  if (n_wanted) PVDB_CUDA(cudaMemcpyAsync(d_wanted, wanted, static_cast<size_t>(n_wanted) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  PVDB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+  const int64_t threads = static_cast<int64_t>(n_words) * 32;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, kNumSMs * 16)));
+  column_filter_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint32_t*>(s->column[column].ptr),
+                                               static_cast<const uint32_t*>(s->active.ptr), d_extra, s->rows, d_wanted,
+                                               n_wanted, d_bits, d_count);
+  PVDB_LAUNCH_CHECK();
+  *d_bits_out = d_bits;
+  *d_count_out = d_count;
+  return PVDB_OK;
+}
+}  // namespace pvdb

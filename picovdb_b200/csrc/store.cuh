@@ -37,6 +37,13 @@ struct Scratch {
 
 }  // namespace pvdb
 
+struct pvdb_store;
+namespace pvdb {
+// (column in wanted) & active (& extra_bits) -> device bitmap + device count (store.cu)
+int build_column_filter(pvdb_store* s, int column, const int32_t* wanted, int n_wanted, const uint32_t* extra_bits,
+                        const uint32_t** d_bits_out, unsigned long long** d_count_out, cudaStream_t st);
+}  // namespace pvdb
+
 struct pvdb_store {
   int device = 0;
   int dim = 0;
@@ -51,6 +58,8 @@ struct pvdb_store {
   pvdb::DeviceBuffer f32;     // capacity x ld_f32 floats, pad columns are zero
   pvdb::DeviceBuffer bf16;    // capacity x ld_bf16 bf16, pad columns are zero
   pvdb::DeviceBuffer active;  // capacity/32 words
+  static constexpr int kMaxColumns = 16;
+  pvdb::DeviceBuffer column[kMaxColumns];  // metadata codes + 1 per row (0 = absent), see pvdb_store_column_write
 
   cudaStream_t stream = nullptr;       // the store's own stream (host entry points)
   cudaStream_t last_stream = nullptr;  // stream of the most recent call (cross-stream ordering)
@@ -72,4 +81,5 @@ struct pvdb_store {
   // Make `s` the stream the store's data is ordered on (inserts an event edge when it changes).
   int use_stream(cudaStream_t s);
   int ensure_capacity(int64_t need_rows, cudaStream_t s);
+  void drop_columns();
 };

@@ -159,6 +159,10 @@ class _ColumnIndex:
         self.codes = np.full(max(len(docs), 16), -1, dtype=np.int32)
         self.n = len(docs)
         self.ok = True
+        # device mirror (engine.column_write): slot number, rows uploaded so far, rows changed since
+        self.dev_slot: Optional[int] = None
+        self.dev_rows = 0
+        self.dev_dirty: set[int] = set()
         for row, doc in enumerate(docs):
             if doc is not None:
                 self.set(row, doc)
@@ -180,6 +184,34 @@ class _ColumnIndex:
             self.codes = grown
         self.n = max(self.n, row + 1)
         self.codes[row] = -1 if doc is None else self._code(doc.get(self.key), True)
+        if self.dev_slot is not None and row < self.dev_rows:
+            self.dev_dirty.add(row)
+
+    def wanted_codes(self, values) -> Optional[list[int]]:
+        """Codes of the filter values that occur in the column (None if the key is unsupported)."""
+        out = []
+        for v in values:
+            c = self._code(v, False)
+            if not self.ok:
+                return None
+            if c >= 0:
+                out.append(c)
+        return out
+
+    def sync_device(self, engine, n: int) -> None:
+        """Bring the device copy of the codes up to date for rows [0, n)."""
+        self.resize(n)
+        if self.dev_dirty and len(self.dev_dirty) * 4 > max(n, 1):
+            self.dev_rows = 0          # cheaper to re-send everything
+            self.dev_dirty.clear()
+        if self.dev_dirty:
+            rows = np.fromiter((r for r in self.dev_dirty if r < n), dtype=np.int64)
+            if rows.size:
+                engine.column_write(self.dev_slot, self.codes[rows], rows=rows)
+            self.dev_dirty.clear()
+        if self.dev_rows < n:
+            engine.column_write(self.dev_slot, self.codes[self.dev_rows:n], row0=self.dev_rows)
+            self.dev_rows = n
 
     def resize(self, n: int) -> None:
         if n > self.n:
@@ -208,6 +240,8 @@ class _ColumnIndex:
         self.codes = np.full(max(len(keep), 16), -1, dtype=np.int32)
         self.codes[: len(keep)] = kept
         self.n = len(keep)
+        self.dev_slot, self.dev_rows = None, 0   # compaction drops the device columns
+        self.dev_dirty.clear()
 
 
 def _default_engine_factory(dim: int, **kw):
@@ -662,6 +696,48 @@ class PicoVectorDB:
                 passed[i] = True
         return passed if ids is None else (mask & passed)
 
+    def _device_where(self, where: Optional[WhereT], ids: Optional[list[Any]]):
+        """(column slot, wanted codes, optional ids mask) when a one-key dict filter can be evaluated
+        on the device, else None (callable filters, unhashable values, engines without columns)."""
+        eng = self._engine
+        if not (isinstance(where, dict) and len(where) == 1 and hasattr(eng, "search_where")):
+            return None
+        ((key, val),) = where.items()
+        if not isinstance(key, str):
+            return None
+        is_in = isinstance(val, dict) and set(val.keys()) == {"$in"}
+        col = self._columns.get(key)
+        if col is None:
+            col = self._columns[key] = _ColumnIndex(key, self._docs)
+        if not col.ok:
+            return None
+        try:
+            wanted = col.wanted_codes(set(val["$in"]) if is_in else (val,))
+        except TypeError:
+            return None
+        if wanted is None:
+            return None
+        if col.dev_slot is None:
+            used = {c.dev_slot for c in self._columns.values() if c.dev_slot is not None}
+            free = [i for i in range(getattr(eng, "MAX_COLUMNS", 16)) if i not in used]
+            if not free:  # all device columns taken: evict one (it is re-sent when used again)
+                victim = next(c for c in self._columns.values() if c.dev_slot is not None)
+                free = [victim.dev_slot]
+                victim.dev_slot, victim.dev_rows = None, 0
+                victim.dev_dirty.clear()
+            col.dev_slot, col.dev_rows = free[0], 0
+            col.dev_dirty.clear()
+        n = len(self._ids)
+        col.sync_device(eng, n)
+        extra = None
+        if ids is not None:
+            extra = np.zeros(n, dtype=bool)
+            for s in ids:
+                row = self._id2idx.get(s)
+                if row is not None:
+                    extra[row] = True
+        return col.dev_slot, wanted, extra
+
     def search(
         self,
         query_vecs: np.ndarray,
@@ -695,21 +771,35 @@ class PicoVectorDB:
         with self._rwlock.read_lock():
             if not self._id2idx:
                 return [[] for _ in range(num_q)]  # also for a single query (reference quirk Q2)
-            mask = self._candidate_mask(where, ids)
-            n_cand = len(self._id2idx) if mask is None else int(np.count_nonzero(mask))
-            if n_cand == 0:
-                return [[] for _ in range(num_q)]
             filtered = ids is not None or where is not None
             base = top_k + self._adaptive_buffer if filtered else top_k
-            k_eff = min(base, n_cand)
+            dev = self._device_where(where, ids) if base >= 1 else None
+            if dev is not None:
+                # dict filter evaluated on the device from the code column: no host mask, no upload
+                slot, wanted, extra = dev
+                if not wanted:
+                    return [[] for _ in range(num_q)]
+                scores, rows, n_cand = self._engine.search_where(
+                    raw, int(base), slot, wanted, extra, precision=self._precision
+                )
+                if n_cand == 0:
+                    return [[] for _ in range(num_q)]
+                k_eff = min(base, n_cand)
+            else:
+                mask = self._candidate_mask(where, ids)
+                n_cand = len(self._id2idx) if mask is None else int(np.count_nonzero(mask))
+                if n_cand == 0:
+                    return [[] for _ in range(num_q)]
+                k_eff = min(base, n_cand)
+                if k_eff < 1:
+                    self._last_k_eff = int(k_eff)
+                    return [[] for _ in range(num_q)]
+                scores, rows = self._engine.search(raw, int(k_eff), mask, precision=self._precision)
             self._last_k_eff = int(k_eff)
             # which numpy strategy the reference would have used; the device does one fused select
             self._last_topk_strategy = (
                 "argsort" if (k_eff / n_cand) > self._argsort_threshold else "argpartition"
             )
-            if k_eff < 1:
-                return [[] for _ in range(num_q)]
-            scores, rows = self._engine.search(raw, int(k_eff), mask, precision=self._precision)
             docs = self._docs
             n_slots = len(self._ids)
             recheck = callable(where)

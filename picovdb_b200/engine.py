@@ -204,6 +204,37 @@ class DeviceStore:
         N.check(self._lib.pvdb_search(self.handle, _ptr(q), nq, k, _ptr(bits), flags, _ptr(scores), _ptr(rows)))
         return scores, rows
 
+    # -- metadata columns (on-device dict `where` filters) ---------------------------------------
+    MAX_COLUMNS = 16
+
+    MAX_COLUMNS = 16  # pvdb_store::kMaxColumns
+
+    def column_write(self, column: int, codes: np.ndarray, rows: Optional[np.ndarray] = None, row0: int = 0) -> None:
+        """codes[i] (int32 >= 0, -1 = absent) for rows[i], or for the consecutive rows from row0."""
+        codes = np.ascontiguousarray(codes, dtype=np.int32)
+        r = None if rows is None else _i64c(rows)
+        N.check(self._lib.pvdb_store_column_write(self.handle, int(column), _ptr(r), int(row0), _ptr(codes),
+                                                  codes.shape[0]))
+
+    def column_drop(self, column: int) -> None:
+        N.check(self._lib.pvdb_store_column_drop(self.handle, int(column)))
+
+    def search_where(self, queries: np.ndarray, k: int, column: int, wanted_codes, extra: Optional[np.ndarray] = None,
+                     precision: str = "auto") -> tuple[np.ndarray, np.ndarray, int]:
+        """Search restricted to rows whose `column` code is in `wanted_codes` (and `extra` mask, if
+        given).  The bitmap is built on the device.  Returns (scores, rows, number of eligible rows)."""
+        q = _f32c(queries)
+        nq = q.shape[0]
+        wanted = np.unique(np.asarray(list(wanted_codes), dtype=np.int32))  # sorted: the kernel bisects
+        bits = None if extra is None else pack_row_mask(extra)
+        scores = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        ncand = C.c_int64(0)
+        N.check(self._lib.pvdb_search_where(self.handle, _ptr(q), nq, int(k), int(column), _ptr(wanted),
+                                            wanted.shape[0], _ptr(bits), N.PRECISIONS[precision], _ptr(scores),
+                                            _ptr(rows), C.byref(ncand)))
+        return scores, rows, int(ncand.value)
+
     def search_dev(self, d_queries: int, nq: int, k: int, d_scores: int, d_rows: int, d_prefilter: int = 0,
                    precision: str = "auto", normalized: bool = False, rescore: bool = True, stream: int = 0,
                    scan_only: bool = False) -> None:

@@ -23,6 +23,7 @@ class HostEngine:
         self.fixed_capacity = fixed_capacity
         self.reserved = int(reserve_rows)
         self.calls: list[str] = []
+        self.columns: dict[int, np.ndarray] = {}
 
     @property
     def rows(self) -> int:
@@ -72,6 +73,7 @@ class HostEngine:
         keep = np.asarray(keep_rows, dtype=np.int64)
         self.vectors = np.ascontiguousarray(self.vectors[keep])
         self.active = np.ones(keep.size, dtype=bool)
+        self.columns.clear()  # like the device store: compaction drops the columns
 
     def fetch_rows(self, rows) -> np.ndarray:
         return self.vectors[np.asarray(rows, dtype=np.int64)].copy()
@@ -99,3 +101,33 @@ class HostEngine:
 
     def set_row_base(self, base: int) -> None:
         self.row_base = int(base)
+
+    # -- metadata columns (mirror of DeviceStore.column_write / search_where) ----------------
+    MAX_COLUMNS = 16
+
+    def column_write(self, column, codes, rows=None, row0=0) -> None:
+        self.calls.append("column_write")
+        col = self.columns.setdefault(column, np.full(0, -1, dtype=np.int32))
+        codes = np.asarray(codes, dtype=np.int32)
+        idx = np.asarray(rows, dtype=np.int64) if rows is not None else np.arange(row0, row0 + codes.size)
+        assert idx.size == 0 or idx.max() < self.rows, "column rows must exist in the store"
+        if col.size < self.rows:
+            col = np.concatenate([col, np.full(self.rows - col.size, -1, dtype=np.int32)])
+        col[idx] = codes
+        self.columns[column] = col
+
+    def column_drop(self, column) -> None:
+        self.columns.pop(column, None)
+
+    def search_where(self, queries, k, column, wanted_codes, extra=None, precision="auto"):
+        self.calls.append("search_where")
+        col = self.columns[column]
+        if col.size < self.rows:
+            col = np.concatenate([col, np.full(self.rows - col.size, -1, dtype=np.int32)])
+        pf = np.isin(col[: self.rows], np.asarray(list(wanted_codes), dtype=np.int32)) & (col[: self.rows] >= 0)
+        if extra is not None:
+            pf &= np.asarray(extra, dtype=bool)[: self.rows]
+        n_cand = int((pf & self.active).sum())
+        qn = O.prepare_queries(queries, self.dim)[0]
+        s, r = O.search(self.vectors, qn, k, self.active, pf)
+        return s, r, n_cand

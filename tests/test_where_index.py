@@ -102,3 +102,75 @@ def test_unhashable_values_fall_back_to_the_loop(make_db):
     assert [r[K_ID] for r in db.query(q, where={"tags": "x"})] == ["b"]
     assert [r[K_ID] for r in db.query(q, where={"tags": ["x", "y"]})] == ["a"]
     assert not db._columns["tags"].ok
+
+
+def _ids_of(res):
+    if res and isinstance(res[0], list):   # no candidates: the reference returns [[]] even for one query
+        return [[r[K_ID] for r in lst] for lst in res]
+    return [r[K_ID] for r in res]
+
+
+def test_device_where_matches_host_mask_path(make_db, monkeypatch):
+    """query(where={...}) through the device-resident code column (pvdb_search_where) returns what
+    the host-mask path returns, through every kind of mutation, with ids=, and keeps quirk Q2's
+    k_eff = min(top_k + buffer, candidates)."""
+    db = make_db(dim=8)
+    rng = np.random.default_rng(3)
+    assert hasattr(db._engine, "search_where")
+
+    def rec(i):
+        return {K_VECTOR: rng.standard_normal(8).astype(np.float32), K_ID: f"r{i}", "cat": i % 4,
+                "tag": "xyz"[i % 3] if i % 5 else None}
+
+    def both(q, **kw):
+        got = db.query(q, **kw)
+        k_eff = db._last_k_eff
+        with monkeypatch.context() as m:
+            m.setattr(PicoVectorDB, "_device_where", lambda self, where, ids: None)
+            want = db.query(q, **kw)
+            assert _ids_of(got) == _ids_of(want), kw
+            if want:
+                assert db._last_k_eff == k_eff
+        return got
+
+    def sweep():
+        q = rng.standard_normal(8).astype(np.float32)
+        for f in ({"cat": 1}, {"cat": {"$in": [0, 3]}}, {"tag": "y"}, {"tag": None}, {"cat": 77}, {"nokey": 1},
+                  {"cat": {"$in": []}}, {"cat": 1.0}):
+            both(q, top_k=6, where=f)
+        some = list(db._id2idx)[::2] + ["ghost"]
+        both(q, top_k=4, where={"cat": 2}, ids=some)
+        both(q, top_k=500, where={"cat": 2})        # more than there are candidates
+        res = db.query(np.stack([q, -q]), top_k=3, where={"cat": 0})
+        assert len(res) == 2 and all(r["cat"] == 0 for lst in res for r in lst)
+
+    db.upsert([rec(i) for i in range(200)])
+    sweep()
+    db.upsert([rec(i) for i in range(200, 260)])                       # appended rows reach the column
+    db.upsert([{K_VECTOR: rng.standard_normal(8), K_ID: "r7", "cat": 1, "tag": "y"}])  # update in place
+    sweep()
+    db.delete([f"r{i}" for i in range(0, 260, 3)])
+    sweep()
+    db.upsert([{K_VECTOR: rng.standard_normal(8), K_ID: f"n{i}", "cat": 1} for i in range(40)])  # slot reuse
+    sweep()
+    db.vacuum()                                                        # compaction drops the device columns
+    assert all(c.dev_slot is None for c in db._columns.values())
+    sweep()
+    assert any(c.dev_slot is not None for c in db._columns.values())
+
+
+def test_device_where_column_eviction(make_db):
+    """More filter keys than device column slots: the oldest column is evicted and re-sent on use."""
+    db = make_db(dim=4)
+    rng = np.random.default_rng(5)
+    keys = [f"k{j}" for j in range(20)]
+    db.upsert([{K_VECTOR: rng.standard_normal(4), K_ID: f"r{i}", **{k: (i + j) % 3 for j, k in enumerate(keys)}}
+               for i in range(50)])
+    q = rng.standard_normal(4).astype(np.float32)
+    for rnd in range(2):
+        for j, k in enumerate(keys):
+            res = db.query(q, top_k=50, where={k: 1})
+            want = {f"r{i}" for i in range(50) if (i + j) % 3 == 1}
+            assert set(_ids_of(res)) == want
+    slots = [c.dev_slot for c in db._columns.values() if c.dev_slot is not None]
+    assert len(slots) == len(set(slots)) <= 16

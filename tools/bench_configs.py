@@ -159,6 +159,32 @@ def main():
             emit(config="C4 5M x 384 fp32, 30% deleted, single query top-10", case=name, ms=ms, qps=1e3 / ms,
                  candidates=int(cand.sum()), algorithmic_bytes=algo, hbm_gbs=algo / ms / 1e6,
                  frac_hbm=algo / ms / 1e6 / hbm, peak=hbm, peak_source=src)
+        # dict `where` filter, end to end through the host calls (host numpy query, host results):
+        # (a) host builds + packs the boolean mask and the library uploads it (pvdb_search),
+        # (b) the filter is evaluated on the device from a resident code column (pvdb_search_where).
+        import time
+        st.column_write(0, cat.astype(np.int32))
+        qh = q1.cpu().numpy()
+        for name, wanted in (("where category in even (50%)", [0, 2, 4, 6, 8]), ("where category == 0 (10%)", [0])):
+            pf = np.isin(cat, wanted)
+            ra = st.search(qh, k, prefilter=pf, precision="f32")[1]
+            _, rb, ncand = st.search_where(qh, k, 0, wanted, precision="f32")
+            assert (ra == rb).all() and ncand == int((pf & active).sum())
+            t0 = time.perf_counter()
+            for _ in range(20):
+                st.search(qh, k, prefilter=np.isin(cat, wanted), precision="f32")
+            ms_a = (time.perf_counter() - t0) / 20 * 1e3
+            t0 = time.perf_counter()
+            for _ in range(20):
+                st.search(qh, k, prefilter=pf, precision="f32")
+            ms_a2 = (time.perf_counter() - t0) / 20 * 1e3
+            t0 = time.perf_counter()
+            for _ in range(100):
+                st.search_where(qh, k, 0, wanted, precision="f32")
+            ms_b = (time.perf_counter() - t0) / 100 * 1e3
+            emit(config="C4 5M x 384 fp32, 30% deleted, single query top-10, host call", case=name,
+                 ms_host_mask_build_pack_upload=ms_a, ms_host_mask_ready_pack_upload=ms_a2, ms_device_where=ms_b,
+                 candidates=ncand)
         st.close()
 
     if "c5s" in args.which or "c5b" in args.which:
