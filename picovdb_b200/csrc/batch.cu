@@ -370,6 +370,18 @@ __device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float
   }
 }
 
+// ---------------------------------------------------------------------------- optional cycle counters
+// -DPVDB_BATCH_STATS (PVDB_NVCC_EXTRA): where the epilogue and MMA warps spend their time; read with
+// pvdb_debug_batch_stats().  Not compiled into the shipped library.
+#ifdef PVDB_BATCH_STATS
+__device__ unsigned long long g_batch_stats[16];
+#define STAT_T(var) const long long var = clock64()
+#define STAT_ADD(slot, val) stat_local[slot] += static_cast<unsigned long long>(val)
+#else
+#define STAT_T(var)
+#define STAT_ADD(slot, val)
+#endif
+
 // ---------------------------------------------------------------------------- the GEMM + top-k kernel
 // PAIR (implies CL == 2): the two CTAs of a cluster form one cta_group::2 MMA unit -- M = 256 (each
 // CTA's own 128-query tile), N = 256 with each CTA holding HALF of the database tile's rows.  A stage
@@ -501,12 +513,20 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+#ifdef PVDB_BATCH_STATS
+      unsigned long long stat_local[16] = {};
+      STAT_T(m_begin);
+#endif
       for (int64_t v = v_first; v < n_visits; v += v_step) {
+        STAT_T(m0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+        STAT_ADD(6, clock64() - m0);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kBN);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          STAT_T(m1);
           mbar_wait(full_bar(stage), phase);
+          STAT_ADD(7, clock64() - m1);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint64_t da = make_smem_desc(a_addr);
@@ -538,6 +558,10 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           acc_phase ^= 1u;
         }
       }
+#ifdef PVDB_BATCH_STATS
+      STAT_ADD(8, clock64() - m_begin);
+      for (int i = 6; i <= 8; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
+#endif
     }
   } else if (warp >= 4) {
     // ======================= epilogue: mask + running top-k =======================
@@ -557,6 +581,10 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
+#ifdef PVDB_BATCH_STATS
+    unsigned long long stat_local[16] = {};
+    STAT_T(e_begin);
+#endif
     for (int64_t v = v_first; v < n_visits; v += v_step) {
       int t, qt;
       if (!decode_unit_visit<CL>(p, v, cta_rank, t, qt)) {
@@ -593,7 +621,14 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN;
       const uint32_t* aw = p.active + (row0 >> 5);
       const uint32_t* pw = p.prefilter ? p.prefilter + (row0 >> 5) : nullptr;
+      STAT_T(e0);
       mbar_wait(tfull_bar(acc), acc_phase);
+      STAT_ADD(1, clock64() - e0);
+      STAT_ADD(9, 1);
+#ifdef PVDB_BATCH_STATS
+      const int cnt_before_visit = cnt;
+      int pruned_away = 0;
+#endif
       tcgen05_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
       uint32_t va[32], vb[32];
@@ -618,6 +653,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         // pools that could overflow during the next 64 columns are pruned now (warp co-operative)
         unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 64);
         if (need) __syncwarp();
+        STAT_T(e1);
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
@@ -625,14 +661,26 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           int nc;
           float nt;
           prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
+          STAT_ADD(3, 1);
           if (lane == src) {
+#ifdef PVDB_BATCH_STATS
+            pruned_away += c - nc;
+#endif
             cnt = nc;
             if (nt > thr) thr = nt;
             if (c >= p.k_sel) atomicMax(gthr, f32_to_ordered(nt));
           }
           __syncwarp();
         }
+        STAT_ADD(2, clock64() - e1);
       }
+#ifdef PVDB_BATCH_STATS
+      {
+        int appended = cnt + pruned_away - cnt_before_visit;
+        for (int o = 16; o > 0; o >>= 1) appended += __shfl_xor_sync(0xffffffffu, appended, o);
+        STAT_ADD(4, appended);
+      }
+#endif
       // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -647,6 +695,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       s_thr[qt * kBM + ql] = thr;
       s_cnt[qt * kBM + ql] = static_cast<uint16_t>(cnt);
     }
+    STAT_ADD(0, clock64() - e_begin);
+    STAT_T(e2);
     // all visits done: leave a sorted, zero-padded list of k_sel keys per (query tile met, query)
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps agree on s_touched
     for (int qt = 0; qt < p.q_tiles; ++qt) {
@@ -664,6 +714,13 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       if (ew == 0 && lane == 0) p.touched[static_cast<size_t>(blockIdx.x) * p.q_tiles + qt] = 1;
     }
+#ifdef PVDB_BATCH_STATS
+    STAT_ADD(5, clock64() - e2);
+    if (lane == 0)
+      for (int i = 0; i <= 5; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
+    if (lane == 0) atomicAdd(&g_batch_stats[9], stat_local[9]);
+    if (lane == 0 && ew == 0 && blockIdx.x == 0) atomicAdd(&g_batch_stats[10], 1ull);
+#endif
   }
 
   tcgen05_fence_before();
@@ -909,7 +966,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     // same final merge, so the result is the exact top k either way.
     int sample_tiles = total_tiles / kSampleFraction;
     if (const char* e = getenv("PVDB_BATCH_SAMPLE")) sample_tiles = atoi(e) > 0 ? total_tiles / atoi(e) : 0;
-    if (static_cast<int64_t>(sample_tiles) * p.q_tiles < 4 * kNumSMs) sample_tiles = 0;  // too small to pay off
+    int64_t min_sample_visits = 4 * kNumSMs;  // below this the sample pass is too small to pay off
+    if (const char* e = getenv("PVDB_BATCH_SAMPLE_MINV")) min_sample_visits = atoll(e);
+    if (static_cast<int64_t>(sample_tiles) * p.q_tiles < min_sample_visits) sample_tiles = 0;
 
     const int grid_max = kNumSMs;  // pools / flags are sized for a full grid
     const size_t pool_bytes = static_cast<size_t>(grid_max) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
@@ -972,3 +1031,13 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
 }
 
 }  // namespace pvdb
+
+#ifdef PVDB_BATCH_STATS
+extern "C" int pvdb_debug_batch_stats(unsigned long long* out, int n, int reset) {
+  unsigned long long zero[16] = {};
+  if (out && n > 0)
+    PVDB_CUDA(cudaMemcpyFromSymbol(out, pvdb::g_batch_stats, sizeof(unsigned long long) * (n < 16 ? n : 16)));
+  if (reset) PVDB_CUDA(cudaMemcpyToSymbol(pvdb::g_batch_stats, zero, sizeof(zero)));
+  return PVDB_OK;
+}
+#endif

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--queries", type=int, default=4096)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="bf16: bf16-only store (C5); tf32: fp32 store, TF32 pass + fp32 re-scoring (C3)")
+    ap.add_argument("--label", default=None)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -44,7 +47,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     r0, r1 = shard_range(args.rows, world, rank)
     n_local = r1 - r0
-    store = DeviceStore(args.dim, device=lr, reserve_rows=n_local, keep_f32=False, bf16_mirror=True)
+    is_bf16 = args.precision == "bf16"
+    store = DeviceStore(args.dim, device=lr, reserve_rows=n_local, keep_f32=not is_bf16, bf16_mirror=is_bf16)
     gen = torch.Generator(device=dev).manual_seed(123 + rank)
     stream = torch.cuda.current_stream().cuda_stream
     chunk = 262144
@@ -56,7 +60,7 @@ def main():
     sh = ShardedSearch(store, r0)
     q = torch.randn(args.queries, args.dim, device=dev, generator=torch.Generator(device=dev).manual_seed(99))
     for _ in range(3):
-        sh.search_dev(q, args.k, precision="bf16")
+        sh.search_dev(q, args.k, precision=args.precision)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -64,7 +68,7 @@ def main():
     for _ in range(args.iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        s, r = sh.search_dev(q, args.k, precision="bf16")
+        s, r = sh.search_dev(q, args.k, precision=args.precision)
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
@@ -79,10 +83,14 @@ def main():
             with open(p) as f:
                 peak = float(json.load(f)["bf16_tflops"])
         flops = 2.0 * args.queries * args.rows * args.dim
+        if not is_bf16:
+            peak = peak / 2  # no measured TF32 peak in MEASURED_PEAKS.json: nominal ratio to bf16
+        label = args.label or ("C5 batch" if is_bf16 else "C3 batch")
         print(json.dumps({
-            "config": f"C5 batch: {args.rows} x {args.dim} bf16 over {world} GPU(s), {args.queries} queries, top-{args.k}",
-            "ms": ms, "qps": args.queries / ms * 1e3, "tflops_aggregate": flops / ms / 1e9,
-            "frac_bf16_peak_aggregate": flops / ms / 1e9 / (peak * world), "peak_per_gpu": peak,
+            "config": f"{label}: {args.rows} x {args.dim} {args.precision} over {world} GPU(s), {args.queries} queries, top-{args.k}",
+            "n_gpus": world, "ms": ms, "qps": args.queries / ms * 1e3, "tflops_aggregate": flops / ms / 1e9,
+            "frac_tensor_peak_aggregate": flops / ms / 1e9 / (peak * world), "peak_per_gpu": peak,
+            "peak_kind": "measured bf16" if is_bf16 else "measured bf16 / 2 (tf32)",
             "rows_ok": bool((r >= 0).all().item() and (r < args.rows).all().item()),
         }), flush=True)
     store.close()

@@ -118,6 +118,18 @@ def main():
                  tflops=flops / ms / 1e9, frac_tf32_peak=flops / ms / 1e9 / tf32_tf, peak_tf32_assumed=tf32_tf,
                  recall_vs_exact=recall_vs_exact(st, q, k, out_r), l2="flushed between iterations")
         st.close()
+        # the reference's README bench draws uniform[0,1) vectors (bench/upserts.py:25): all cosines
+        # sit near 0.75 with rank gaps ~2e-4, the hard case for the TF32 pass + fp32 re-scoring
+        st = DeviceStore(dim, device=0, reserve_rows=rows)
+        ugen = torch.Generator(device=dev).manual_seed(123)
+        x = torch.rand(rows, dim, device=dev, generator=ugen)
+        st.upsert_range_dev(x.data_ptr(), 0, rows, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        qu = torch.rand(nq, dim, device=dev, generator=ugen)
+        ms, _, out_r = time_search(st, qu, k, "tf32", iters=20, flush=l2buf)
+        emit(config="C1 100k x 1024 fp32 uniform[0,1) (README bench data), 1000-query batch, top-10", path="tf32",
+             ms=ms, qps=nq / ms * 1e3, recall_vs_exact=recall_vs_exact(st, qu, k, out_r))
+        st.close()
 
     if "c3" in args.which:
         rows, dim, nq, k = int(10_000_000 * args.scale), 768, 4096, 100
