@@ -3,7 +3,7 @@
 //     scores = vecs @ V.T ; argpartition ; argsort        (picovdb/pico_vdb.py:683-714)
 // without ever writing the Q x N score matrix to HBM.
 //
-// Structure (one persistent CTA per SM, 256 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: cp.async.bulk.tensor loads a 128-row query tile slice (A) and a
 //               256-row database tile slice (B), 128 bytes of K each, into a 4-stage shared-memory
 //               ring (128B swizzle), completion on mbarriers.
@@ -11,13 +11,16 @@
 //               kind::f16 on the bf16 mirror), M=128 x N=256, accumulating in TMEM; tcgen05.commit
 //               releases ring slots and publishes finished accumulators.  TMEM holds two
 //               accumulators (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of i+1.
-//   warps 4-7   epilogue: thread t owns query t of the tile (TMEM lane t).  It streams the 256
-//               scores of each tile out of TMEM (tcgen05.ld 32x32b.x32, next chunk in flight while
-//               the current one is examined), turns masked columns into -inf, and compares the
-//               MAXIMUM of each 8-column group with its running threshold; only groups that beat it
-//               are examined column by column and appended to the query's candidate pool.  When a
-//               pool fills, the warp sorts it co-operatively (bitonic network in registers), keeps
-//               the best k_sel and raises the threshold.
+//   warps 4-11  epilogue: two warps per TMEM lane quarter, one per 128-column HALF of the
+//               accumulator (the tcgen05.ld round trip, not instruction issue, bounds one warp; two
+//               warps per SM sub-partition keep two loads in flight).  Thread t of a warp owns query
+//               t of the tile (TMEM lane t) for its half: it streams its 128 scores out of TMEM
+//               (tcgen05.ld 32x32b.x32, next chunk in flight while the current one is examined),
+//               turns masked columns into -inf, and compares the MAXIMUM of each 8-column group
+//               with the query's running threshold; only groups that beat it are examined column by
+//               column and appended to the (query, half) candidate pool.  When a pool fills, the
+//               warp sorts it co-operatively (bitonic network in registers), keeps the best k_sel
+//               and raises the threshold, which both halves share through shared memory.
 //
 // Schedule: a "visit" is (database tile t, query tile qt); visits are numbered tile-major
 // (v = t * q_tiles + qt) and CTA b takes v = b, b + grid, b + 2*grid, ...  At any moment the 148
@@ -25,8 +28,9 @@
 // once and then served to the other query tiles from L2 (the first version walked one query tile
 // down a long chunk of database tiles per CTA; CTAs drifted apart and the 10M x 768 case re-read
 // the database 24x from HBM).  A CTA keeps one running (threshold, count, pool) per query tile it
-// meets; at the end it leaves a sorted list of k_sel keys per (CTA, query tile, query).
-// finalize_batch_kernel merges those lists per query, re-scores the survivors exactly in fp32
+// meets; at the end it leaves each pool as it is (unsorted, with its count).
+// finalize_batch_kernel streams those pools per query through a threshold filter (the best published
+// k_sel-th score is a proven lower bound), sorts what survives, re-scores the best exactly in fp32
 // against the fp32 matrix (tensor-core inputs are rounded to tf32 / bf16; the north star asks for
 // 1e-5 fp32 scores) and writes the top k.
 //
@@ -35,6 +39,8 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "batch.cuh"
@@ -50,7 +56,9 @@ constexpr int kStages = 4;
 constexpr int kStageABytes = kBM * kKBytes;  // 16 KB
 constexpr int kStageBBytes = kBN * kKBytes;  // 32 KB
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
-constexpr int kBatchThreads = 256;
+constexpr int kEpiHalves = 2;       // epilogue warps per TMEM lane quarter (each owns kBN / 2 columns)
+constexpr int kEpiThreads = 128 * kEpiHalves;
+constexpr int kBatchThreads = 128 + kEpiThreads;
 constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
 constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom + 32 slots)
 constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
@@ -60,11 +68,14 @@ constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the databa
 // SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
 // C5 batch: 34.9 vs 32.4 ms), so it stays opt-in.
 constexpr bool kPairDefault = false;
+constexpr int kClusterDefault = 2;  // CTAs per cluster sharing a database tile; 4 and 8 work but measured 3 % / 10 % slower
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
-// shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 f32][cnt: 32 x 128 u16][touched: 32 B]
+// shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 ordered u32][cnt: 2 x 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
-constexpr size_t kStateBytes = static_cast<size_t>(kMaxQTiles) * kBM * (sizeof(float) + sizeof(uint16_t)) + kMaxQTiles;
+constexpr size_t kStateBytes =
+    static_cast<size_t>(kMaxQTiles) * kBM * (sizeof(uint32_t) + kEpiHalves * sizeof(uint16_t)) + kMaxQTiles;
 constexpr size_t kBatchSmem = 1024 /*align*/ + kRingBytes + 256 + kStateBytes;
+static_assert(kBatchSmem <= 227 * 1024, "the batch kernel's shared memory must fit one SM");
 
 struct BatchParams {
   int64_t nq;            // queries in this launch (<= 4096)
@@ -76,7 +87,8 @@ struct BatchParams {
   int pool_cap;          // 64 / 128 / 256 keys per (CTA, query tile, query)
   const uint32_t* active;
   const uint32_t* prefilter;
-  uint64_t* pools;       // [grid][q_tiles][128][pool_cap]
+  uint64_t* pools;       // [grid][q_tiles][half][128][pool_cap]
+  uint16_t* counts;      // [grid][q_tiles][half][128]: keys left in each pool (written for touched tiles)
   uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
   uint32_t* shared_thr;  // [nq] ordered-int image of the best published k_sel-th score (zeroed)
   int tile_begin;        // first database tile of this launch (n_tiles counts from here)
@@ -84,6 +96,8 @@ struct BatchParams {
                          // else a multiple of the query-tile(-pair) count: unit u keeps ONE query tile
                          // and units >= visit_stride stay idle (cheap cold start for the sample pass)
   const float* init_thr; // optional [nq]: a proven lower bound of each query's k_sel-th best score
+  float* dump;           // seed pass only: [q_tiles * 128][dump_ld] masked tensor-core scores are written
+  int dump_ld;           //   here (column = row - tile_begin * 256) instead of being selected
 };
 
 // Visit numbering is tile-major: v = t * q_tiles + qt.
@@ -269,60 +283,79 @@ __host__ __device__ constexpr uint32_t make_idesc(bool bf16, int m = kBM) {
 }
 
 // ---------------------------------------------------------------------------- warp bitonic sort
-// 32*NI keys, element e = i*32 + lane, sorted descending.
+// 32*NI keys, element e = i*32 + lane, sorted descending.  The cross-lane stages run as ROLLED loops
+// over (size, stride) with the NI keys of a lane statically indexed: the fully unrolled network was
+// ~3000 instructions (48 KB) of straight-line code that missed the instruction cache on every prune
+// (measured 11-16k cycles per prune of 256 keys).
 template <int NI>
-__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[NI], int lane) {
+__device__ __forceinline__ void warp_cross_stage(uint64_t (&key)[NI], int lane, int size, int stride) {
+  const bool lower = (lane & stride) == 0;
 #pragma unroll
-  for (int size = 2; size <= 32 * NI; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 32) {
-        const int sj = stride >> 5;
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          if ((i & sj) == 0) {
-            const int e = i * 32 + lane;
-            const bool desc = (e & size) == 0;
-            const uint64_t a = key[i], b = key[i | sj];
-            if ((a < b) == desc) {
-              key[i] = b;
-              key[i | sj] = a;
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int e = i * 32 + lane;
-          const uint64_t other = shfl_xor_u64(key[i], stride);
-          const bool desc = (e & size) == 0;
-          const bool lower = (lane & stride) == 0;
-          const bool take_max = (desc == lower);
-          const uint64_t mx = key[i] > other ? key[i] : other;
-          const uint64_t mn = key[i] > other ? other : key[i];
-          key[i] = take_max ? mx : mn;
-        }
-      }
-    }
+  for (int i = 0; i < NI; ++i) {
+    const uint64_t other = shfl_xor_u64(key[i], stride);
+    const bool desc = ((i * 32 + lane) & size) == 0;
+    // the lower lane of a descending pair keeps the larger key
+    const bool take_max = (desc == lower);
+    if ((key[i] < other) == take_max) key[i] = other;
   }
 }
 
-// Co-operative prune of one query's pool: keep the best k_sel keys (sorted, zero padded, at the
-// front).  Returns (through the references) the pool's new count and threshold.
 template <int NI>
-__device__ __forceinline__ void prune_pool(uint64_t* pool, int count, int k_sel, int lane, int& new_count,
+__device__ __forceinline__ void warp_sort_desc(uint64_t (&key)[NI], int lane) {
+  // sizes 2..32: only cross-lane stages
+#pragma unroll 1
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) warp_cross_stage<NI>(key, lane, size, stride);
+  }
+  // sizes 64..32*NI: a few in-register stages (static indices), then the five cross-lane stages
+#pragma unroll
+  for (int size = 64; size <= 32 * NI; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride >= 32; stride >>= 1) {
+      const int sj = stride >> 5;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        if ((i & sj) == 0) {
+          const bool desc = ((i * 32) & size) == 0;
+          const uint64_t a = key[i], b = key[i | sj];
+          if ((a < b) == desc) {
+            key[i] = b;
+            key[i | sj] = a;
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int stride = 16; stride > 0; stride >>= 1) warp_cross_stage<NI>(key, lane, size, stride);
+  }
+}
+
+// Pools of the 32 queries of a warp are interleaved sector by sector: slot s of lane l lives at
+// key index ((s / 4) * 32 + l) * 4 + s % 4 of the warp's block of 32 * pool_cap keys.  While a tile
+// is examined with no threshold yet (cold start) all lanes append in lock step and a warp-wide
+// append touches 8 consecutive 128-byte lines instead of 32 scattered ones; the readers (prune,
+// finalize) still get whole 32-byte sectors of one query.
+__device__ __forceinline__ size_t pool_slot(int lane, int s) {
+  return (static_cast<size_t>(s >> 2) * 32 + lane) * 4 + (s & 3);
+}
+
+// Co-operative prune of the pool of lane `src`: keep the best k_sel keys (sorted, at the front).
+// Returns (through the references) the pool's new count and threshold.
+template <int NI>
+__device__ __forceinline__ void prune_pool(uint64_t* wpool, int src, int count, int k_sel, int lane, int& new_count,
                                            float& new_thr) {
   uint64_t key[NI];
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int e = i * 32 + lane;
-    key[i] = (e < count) ? pool[e] : 0ull;
+    key[i] = (e < count) ? wpool[pool_slot(src, e)] : 0ull;
   }
   warp_sort_desc<NI>(key, lane);
 #pragma unroll
   for (int i = 0; i < NI; ++i) {
     const int e = i * 32 + lane;
-    if (e < k_sel) pool[e] = key[i];
+    if (e < k_sel) wpool[pool_slot(src, e)] = key[i];
   }
   // k-th key (entry k_sel-1) decides the new threshold
   const int ke = k_sel - 1;
@@ -337,8 +370,8 @@ __device__ __forceinline__ void prune_pool(uint64_t* pool, int count, int k_sel,
 
 // One 32-column chunk of scores for this thread's query: masked columns become -inf, then only
 // 8-column groups whose maximum beats the threshold are examined column by column.
-__device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float thr, uint64_t* pool, int& cnt,
-                                           uint32_t row_base) {
+__device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float thr, uint64_t* wpool, int lane,
+                                           int& cnt, uint32_t row_base) {
   if (mw != 0xffffffffu) {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -361,7 +394,7 @@ __device__ __forceinline__ void scan_chunk(uint32_t (&v)[32], uint32_t mw, float
         for (int j = 0; j < 8; ++j) {
           const float sc = __uint_as_float(v[q * 8 + j]);
           if (sc > thr) {
-            pool[cnt] = make_key(sc, row_base + q * 8 + j);
+            wpool[pool_slot(lane, cnt)] = make_key(sc, row_base + q * 8 + j);
             ++cnt;
           }
         }
@@ -404,9 +437,9 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRingBytes);
   // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 4);
-  float* s_thr = reinterpret_cast<float*>(smem + kRingBytes + 256);                   // [q_tiles][128]
-  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_thr + kMaxQTiles * kBM);            // [q_tiles][128]
-  uint8_t* s_touched = reinterpret_cast<uint8_t*>(s_cnt + kMaxQTiles * kBM);          // [q_tiles]
+  uint32_t* s_thr = reinterpret_cast<uint32_t*>(smem + kRingBytes + 256);              // [q_tiles][128] ordered
+  uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_thr + kMaxQTiles * kBM);            // [half][q_tiles][128]
+  uint8_t* s_touched = reinterpret_cast<uint8_t*>(s_cnt + kEpiHalves * kMaxQTiles * kBM);  // [q_tiles]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -432,7 +465,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), PAIR ? 8 : 4);  // one arrival per epilogue warp (of both CTAs for a pair)
+      // one arrival per epilogue warp (of both CTAs for a pair)
+      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * kEpiHalves);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -565,20 +599,25 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ======================= epilogue: mask + running top-k =======================
-    const int ew = warp - 4;          // == warp % 4: the TMEM lane quarter this warp may read
-    const int ql = ew * 32 + lane;    // query (TMEM lane) owned by this thread
+    const int ew = warp & 3;                 // the TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;        // which 128 columns of the accumulator it examines
+    const int ql = ew * 32 + lane;           // query (TMEM lane) owned by this thread
+    uint16_t* my_cnt = s_cnt + half * (kMaxQTiles * kBM);
     for (int qt = 0; qt < p.q_tiles; ++qt) {
-      const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
-      float t0 = -INFINITY;
-      if (live && p.init_thr != nullptr) {
-        // scores equal to the bound must still be admitted: start one ulp below it
-        const float b = p.init_thr[static_cast<int64_t>(qt) * kBM + ql];
-        if (b > -INFINITY) t0 = ordered_to_f32(f32_to_ordered(b) - 1u);
+      if (half == 0) {
+        const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
+        uint32_t t0 = f32_to_ordered(-INFINITY);
+        if (live && p.init_thr != nullptr) {
+          // scores equal to the bound must still be admitted: start one ulp below it
+          const float b = p.init_thr[static_cast<int64_t>(qt) * kBM + ql];
+          if (b > -INFINITY) t0 = f32_to_ordered(b) - 1u;
+        }
+        s_thr[qt * kBM + ql] = live ? t0 : f32_to_ordered(INFINITY);  // padding queries never collect candidates
       }
-      s_thr[qt * kBM + ql] = live ? t0 : INFINITY;  // padding queries never collect candidates
-      s_cnt[qt * kBM + ql] = 0;
+      my_cnt[qt * kBM + ql] = 0;
     }
-    uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * kBM * p.pool_cap;
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // both halves see the initial thresholds
+    uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * (kEpiHalves * kBM) * p.pool_cap;
     int acc = 0;
     uint32_t acc_phase = 0;
 #ifdef PVDB_BATCH_STATS
@@ -603,53 +642,75 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         continue;
       }
-      uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
-      uint64_t* pool = warp_pools + static_cast<size_t>(lane) * p.pool_cap;
-      float thr = s_thr[qt * kBM + ql];
-      int cnt = s_cnt[qt * kBM + ql];
-      if (lane == 0 && ew == 0) s_touched[qt] = 1;
+      uint64_t* warp_pools = cta_pools + ((static_cast<size_t>(qt) * kEpiHalves + half) * kBM + ew * 32) * p.pool_cap;
+      // The threshold of a query is shared by its two halves (and, below, by all CTAs): whoever
+      // holds k_sel candidates proves a lower bound of the final k_sel-th best for everybody.
+      const uint32_t thr_in = s_thr[qt * kBM + ql];
+      float thr = ordered_to_f32(thr_in);
+      int cnt = my_cnt[qt * kBM + ql];
+      if (lane == 0 && warp == 4) s_touched[qt] = 1;
       // Shared threshold: every CTA that holds k_sel candidates for this query publishes its k_sel-th
       // score (atomicMax below).  The global k_sel-th best is >= each of them, so anything strictly
       // below the published maximum can be skipped by everybody; without this each of the ~37 CTAs
       // serving a query tile warms its threshold up on its own and collects ~37x more candidates.
       const int64_t gq = static_cast<int64_t>(qt) * kBM + ql;
       uint32_t* gthr = p.shared_thr + (gq < p.nq ? gq : 0);
-      {
-        const uint32_t g = __ldcg(gthr);
-        if (gq < p.nq && g > 1u) thr = fmaxf(thr, ordered_to_f32(g - 1u));  // keep scores >= published
+      // loads whose latency hides behind the wait for the accumulator: published threshold and the
+      // mask words of this half (4 words = 128 rows; the active bitmap is allocated up to capacity,
+      // the prefilter only has ceil(rows / 32) words)
+      const uint32_t g_pub = __ldcg(gthr);
+      const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN + half * (kBN / kEpiHalves);
+      constexpr int kChunks = kBN / kEpiHalves / 32;  // 32-column chunks per half
+      static_assert(kChunks == 4, "mask words of a half are fetched as one uint4");
+      const uint4 aw4 = __ldg(reinterpret_cast<const uint4*>(p.active + (row0 >> 5)));
+      uint32_t mwords[kChunks] = {aw4.x, aw4.y, aw4.z, aw4.w};
+      if (p.prefilter != nullptr) {
+        const int64_t n_pw = (p.n_rows + 31) >> 5;
+#pragma unroll
+        for (int i = 0; i < kChunks; ++i) {
+          const int64_t w = (row0 >> 5) + i;
+          mwords[i] &= (w < n_pw) ? __ldg(p.prefilter + w) : 0u;
+        }
       }
-      const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN;
-      const uint32_t* aw = p.active + (row0 >> 5);
-      const uint32_t* pw = p.prefilter ? p.prefilter + (row0 >> 5) : nullptr;
       STAT_T(e0);
       mbar_wait(tfull_bar(acc), acc_phase);
       STAT_ADD(1, clock64() - e0);
+      if (gq < p.nq && g_pub > 1u) thr = fmaxf(thr, ordered_to_f32(g_pub - 1u));  // keep scores >= published
       STAT_ADD(9, 1);
 #ifdef PVDB_BATCH_STATS
       const int cnt_before_visit = cnt;
       int pruned_away = 0;
 #endif
       tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN);
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                              static_cast<uint32_t>(acc * kBN + half * (kBN / kEpiHalves));
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr0, va);
-#pragma unroll 1
-      for (int cb = 0; cb < kBN / 32; cb += 2) {
-        // Mask words of the two 32-column chunks of this step (warp-uniform).  Active words exist up
-        // to the allocated capacity and are zero past the last row; the prefilter only has
-        // ceil(rows/32) words, so it is consulted only where a row is active.
-        uint32_t mw0 = __ldg(aw + cb), mw1 = __ldg(aw + cb + 1);
-        if (pw != nullptr) {
-          if (mw0 != 0u) mw0 &= __ldg(pw + cb);
-          if (mw1 != 0u) mw1 &= __ldg(pw + cb + 1);
+      if (p.dump != nullptr) {
+        // seed pass: the masked scores themselves are wanted (seed_threshold_kernel selects from them)
+        float* drow = p.dump + static_cast<size_t>(gq) * p.dump_ld + (static_cast<size_t>(t) * kBN + half * (kBN / kEpiHalves));
+#pragma unroll
+        for (int cb = 0; cb < kChunks; ++cb) {
+          tmem_ld_wait(va);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) vb[j] = ((mwords[cb] >> j) & 1u) ? va[j] : 0xff800000u;
+          if (cb + 1 < kChunks) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 1) * 32), va);
+          uint4* d4 = reinterpret_cast<uint4*>(drow + cb * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) d4[j] = make_uint4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]);
         }
+      } else {
+#pragma unroll 1
+      for (int cb = 0; cb < kChunks; cb += 2) {
+        // mask words of the two 32-column chunks of this step (warp-uniform)
+        const uint32_t mw0 = cb == 0 ? mwords[0] : mwords[2], mw1 = cb == 0 ? mwords[1] : mwords[3];
         // chunk cb is in flight into `va`; start chunk cb+1 into `vb` before examining `va`
         tmem_ld_wait(va);
         tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 1) * 32), vb);
-        if (mw0 != 0u) scan_chunk(va, mw0, thr, pool, cnt, static_cast<uint32_t>(row0) + cb * 32);
+        if (mw0 != 0u) scan_chunk(va, mw0, thr, warp_pools, lane, cnt, static_cast<uint32_t>(row0) + cb * 32);
         tmem_ld_wait(vb);
-        if (cb + 2 < kBN / 32) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 2) * 32), va);
-        if (mw1 != 0u) scan_chunk(vb, mw1, thr, pool, cnt, static_cast<uint32_t>(row0) + (cb + 1) * 32);
+        if (cb + 2 < kChunks) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 2) * 32), va);
+        if (mw1 != 0u) scan_chunk(vb, mw1, thr, warp_pools, lane, cnt, static_cast<uint32_t>(row0) + (cb + 1) * 32);
         // pools that could overflow during the next 64 columns are pruned now (warp co-operative)
         unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 64);
         if (need) __syncwarp();
@@ -660,7 +721,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const int c = __shfl_sync(0xffffffffu, cnt, src);
           int nc;
           float nt;
-          prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
+          prune_pool<NI>(warp_pools, src, c, p.k_sel, lane, nc, nt);
           STAT_ADD(3, 1);
           if (lane == src) {
 #ifdef PVDB_BATCH_STATS
@@ -674,6 +735,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         }
         STAT_ADD(2, clock64() - e1);
       }
+      }  // select (not dump)
 #ifdef PVDB_BATCH_STATS
       {
         int appended = cnt + pruned_away - cnt_before_visit;
@@ -692,34 +754,27 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         acc = 0;
         acc_phase ^= 1u;
       }
-      s_thr[qt * kBM + ql] = thr;
-      s_cnt[qt * kBM + ql] = static_cast<uint16_t>(cnt);
+      // The other half may be one visit ahead or behind, so a bound proven here is shared NON-strictly
+      // (one ulp lower): a row with exactly the k_sel-th score must not be dropped there, it could
+      // have the lower row number and win the tie.
+      const uint32_t thr_out = f32_to_ordered(thr) - 1u;
+      if (thr_out > thr_in) atomicMax(&s_thr[qt * kBM + ql], thr_out);
+      my_cnt[qt * kBM + ql] = static_cast<uint16_t>(cnt);
     }
     STAT_ADD(0, clock64() - e_begin);
-    STAT_T(e2);
-    // all visits done: leave a sorted, zero-padded list of k_sel keys per (query tile met, query)
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps agree on s_touched
+    // all visits done: the pools stay as they are (finalize filters and sorts); publish their counts
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the epilogue warps agree on s_touched
     for (int qt = 0; qt < p.q_tiles; ++qt) {
-      if (!s_touched[qt]) continue;
-      uint64_t* warp_pools = cta_pools + (static_cast<size_t>(qt) * kBM + ew * 32) * p.pool_cap;
-      const int cnt = s_cnt[qt * kBM + ql];
-      __syncwarp();
-      for (int src = 0; src < 32; ++src) {
-        const int c = __shfl_sync(0xffffffffu, cnt, src);
-        int nc;
-        float nt;
-        prune_pool<NI>(warp_pools + static_cast<size_t>(src) * p.pool_cap, c, p.k_sel, lane, nc, nt);
-        (void)nc;
-        (void)nt;
-      }
-      if (ew == 0 && lane == 0) p.touched[static_cast<size_t>(blockIdx.x) * p.q_tiles + qt] = 1;
+      if (!s_touched[qt] || p.dump != nullptr) continue;
+      const size_t u = static_cast<size_t>(blockIdx.x) * p.q_tiles + qt;
+      p.counts[(u * kEpiHalves + half) * kBM + ql] = my_cnt[qt * kBM + ql];
+      if (warp == 4 && lane == 0) p.touched[u] = 1;
     }
 #ifdef PVDB_BATCH_STATS
-    STAT_ADD(5, clock64() - e2);
     if (lane == 0)
-      for (int i = 0; i <= 5; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
+      for (int i = 0; i <= 4; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
     if (lane == 0) atomicAdd(&g_batch_stats[9], stat_local[9]);
-    if (lane == 0 && ew == 0 && blockIdx.x == 0) atomicAdd(&g_batch_stats[10], 1ull);
+    if (lane == 0 && warp == 4 && blockIdx.x == 0) atomicAdd(&g_batch_stats[10], 1ull);
 #endif
   }
 
@@ -737,10 +792,14 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------- finalize
-// One block per query: merge the per-CTA lists (block bitonic sort in shared memory, in rounds
-// when the lists do not fit at once), re-score the best k_sel rows exactly in fp32 and emit top k.
+// One block per query.  The candidate pools of every (CTA, half) that met the query's tile are
+// streamed through a filter -- a key survives if its score reaches the best lower bound known for the
+// query's k_sel-th best (published threshold, sample-pass bound, or the k_sel-th key of what has been
+// merged so far) -- into a shared-memory buffer that is sorted (block bitonic network) and cut to
+// k_sel whenever it could overflow.  The best k_sel rows are then re-scored exactly in fp32 and the
+// top k written.  Keys are unique, so the result does not depend on the order of arrival.
 constexpr int kFinalThreads = 256;
-constexpr int kFinalCap = 4096;  // keys sorted per round (32 KB of shared memory)
+constexpr int kFinalCap = 4096;  // keys held in shared memory (32 KB)
 
 __device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n_pow2) {
   for (int size = 2; size <= n_pow2; size <<= 1) {
@@ -761,16 +820,27 @@ __device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n_pow2) {
   __syncthreads();
 }
 
+// sort keys[0..n) descending (n <= kFinalCap); entries past n up to the next power of two are zeroed
+__device__ __forceinline__ void block_sort_prefix(uint64_t* keys, int n) {
+  int n_pow2 = 2;
+  while (n_pow2 < n) n_pow2 <<= 1;
+  __syncthreads();
+  for (int i = n + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
+  block_sort_desc(keys, n_pow2);
+}
+
 __global__ void __launch_bounds__(kFinalThreads)
-finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restrict__ touched, int n_ctas,
-                      int pool_cap, int k_sel, int q_tiles, int64_t nq, int k, const float* __restrict__ qn, int ldq,
-                      const float* __restrict__ f32, int ld32, int rescore, int64_t row_base,
-                      float* __restrict__ out_scores, int64_t* __restrict__ out_rows,
-                      const uint64_t* __restrict__ carry_in, uint64_t* __restrict__ carry_out,
-                      float* __restrict__ thr_out) {
+finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __restrict__ counts,
+                      const uint8_t* __restrict__ touched, int n_ctas, int pool_cap, int k_sel, int q_tiles,
+                      int64_t nq, int k, const float* __restrict__ qn, int ldq, const float* __restrict__ f32,
+                      int ld32, int rescore, int64_t row_base, float* __restrict__ out_scores,
+                      int64_t* __restrict__ out_rows, const uint64_t* __restrict__ carry_in,
+                      uint64_t* __restrict__ carry_out, float* __restrict__ thr_out,
+                      const uint32_t* __restrict__ shared_thr, const float* __restrict__ init_thr) {
   __shared__ uint64_t keys[kFinalCap];
   __shared__ int s_lists[kNumSMs];
   __shared__ int s_nlists;
+  __shared__ int s_n;
   const int64_t q = blockIdx.x;
   const int qt = static_cast<int>(q / kBM);
   const int ql = static_cast<int>(q % kBM);
@@ -780,36 +850,59 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restr
       if (touched[static_cast<size_t>(b) * q_tiles + qt]) s_lists[n++] = b;
     s_nlists = n;
   }
-  __syncthreads();
-  const int n_lists = s_nlists;
-  const int lists_per_round = (kFinalCap - k_sel) / k_sel;  // >= 1 since k_sel <= 224
-  int kept = 0;  // keys[0..kept) = best so far (sorted)
+  // lower bound (ordered image) every surviving key must reach
+  uint32_t lb = 0u;
+  {
+    const uint32_t g = shared_thr[q];
+    if (g > 1u) lb = g;
+    if (init_thr != nullptr) {
+      const float b = init_thr[q];
+      if (b > -INFINITY) lb = max(lb, f32_to_ordered(b));
+    }
+  }
+  int n_keys = 0;  // keys[0..n_keys) hold the survivors so far (block-uniform)
   if (carry_in != nullptr) {
     // the sample pass already produced a sorted (zero padded) list of k_sel keys for this query
     for (int j = threadIdx.x; j < k_sel; j += blockDim.x) keys[j] = carry_in[q * k_sel + j];
-    kept = k_sel;
-    __syncthreads();
+    n_keys = k_sel;
   }
-  for (int c0 = 0; c0 < n_lists; c0 += lists_per_round) {
-    const int c1 = min(n_lists, c0 + lists_per_round);
-    const int fresh = (c1 - c0) * k_sel;
-    for (int i = threadIdx.x; i < fresh; i += blockDim.x) {
-      const int c = c0 + i / k_sel, j = i % k_sel;
-      const size_t u = static_cast<size_t>(s_lists[c]) * q_tiles + qt;
-      keys[kept + i] = pools[(u * kBM + ql) * pool_cap + j];
+  if (threadIdx.x == 0) s_n = n_keys;
+  __syncthreads();
+  const int n_pools = s_nlists * kEpiHalves;
+  int c = 0;
+  while (c < n_pools) {
+    // every pool taken this round may contribute up to pool_cap keys
+    const int take = min(n_pools - c, (kFinalCap - n_keys) / pool_cap);
+    if (take == 0) {
+      // buffer (nearly) full: sort, keep the best k_sel, tighten the bound
+      block_sort_prefix(keys, n_keys);
+      n_keys = min(n_keys, k_sel);
+      if (n_keys == k_sel && keys[k_sel - 1] != 0ull) lb = max(lb, static_cast<uint32_t>(keys[k_sel - 1] >> 32));
+      __syncthreads();
+      if (threadIdx.x == 0) s_n = n_keys;
+      __syncthreads();
+      continue;
     }
-    const int filled = kept + fresh;
-    int n_pow2 = 2;
-    while (n_pow2 < filled) n_pow2 <<= 1;
-    for (int i = filled + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
-    block_sort_desc(keys, n_pow2);
-    kept = min(filled, k_sel);
+    for (int i = threadIdx.x; i < take * pool_cap; i += blockDim.x) {
+      const int pi = c + i / pool_cap, j = i % pool_cap;
+      const size_t u = static_cast<size_t>(s_lists[pi / kEpiHalves]) * q_tiles + qt;
+      const size_t slot = (u * kEpiHalves + (pi % kEpiHalves)) * kBM + ql;
+      if (j < static_cast<int>(counts[slot])) {
+        // the 32 pools of an epilogue warp are interleaved (pool_slot)
+        const uint64_t key = pools[(slot & ~size_t(31)) * pool_cap + pool_slot(ql & 31, j)];
+        if (key != 0ull && static_cast<uint32_t>(key >> 32) >= lb) keys[atomicAdd(&s_n, 1)] = key;
+      }
+    }
+    __syncthreads();
+    n_keys = s_n;
+    c += take;
   }
+  block_sort_prefix(keys, n_keys);
+  const int kept = min(n_keys, k_sel);
   // keys[0..kept) sorted descending by tensor-core score
   if (carry_out != nullptr) {
     // sample pass: hand the merged list and its k_sel-th score (a proven lower bound of the final
     // k_sel-th best) to the main pass instead of producing results
-    __syncthreads();
     for (int j = threadIdx.x; j < k_sel; j += blockDim.x) carry_out[q * k_sel + j] = (j < kept) ? keys[j] : 0ull;
     if (threadIdx.x == 0) {
       const uint64_t kth = (kept >= k_sel) ? keys[k_sel - 1] : 0ull;
@@ -821,9 +914,8 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restr
     // exact fp32 dot product of the query with each surviving row (one warp per candidate)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4* q4 = reinterpret_cast<const float4*>(qn + q * ldq);
-    __syncthreads();
-    for (int c = warp; c < kept; c += kFinalThreads / 32) {
-      const uint64_t key = keys[c];
+    for (int cnd = warp; cnd < kept; cnd += kFinalThreads / 32) {
+      const uint64_t key = keys[cnd];
       if (key == 0ull) continue;
       const uint32_t row = key_row(key);
       const float4* v4 = reinterpret_cast<const float4*>(f32 + static_cast<size_t>(row) * ld32);
@@ -838,19 +930,50 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint8_t* __restr
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) keys[c] = make_key(acc, row);
+      if (lane == 0) keys[cnd] = make_key(acc, row);
     }
-    __syncthreads();
-    int n_pow2 = 2;
-    while (n_pow2 < kept) n_pow2 <<= 1;
-    for (int i = kept + threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = 0ull;
-    block_sort_desc(keys, n_pow2);
+    block_sort_prefix(keys, kept);
   }
-  __syncthreads();
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const uint64_t key = (j < kept) ? keys[j] : 0ull;
     out_scores[q * k + j] = key ? key_score(key) : -INFINITY;
     out_rows[q * k + j] = key ? row_base + static_cast<int64_t>(key_row(key)) : -1ll;
+  }
+}
+
+// ---------------------------------------------------------------------------- seed thresholds
+// One block per query: the k_sel-th largest of the query's `n` dumped scores (masked ones are -inf) is
+// a proven lower bound of its final k_sel-th best tensor-core score -- the main pass starts from it
+// instead of -inf.  n <= kSeedCols, sorted descending in shared memory.
+constexpr int kSeedTiles = 2;
+constexpr int kSeedCols = kSeedTiles * kBN;
+constexpr int kSeedThreads = 128;
+
+__global__ void __launch_bounds__(kSeedThreads)
+seed_threshold_kernel(const float* __restrict__ dump, int dump_ld, int n, int k_sel, float* __restrict__ thr_out) {
+  __shared__ uint32_t v[kSeedCols];
+  const int64_t q = blockIdx.x;
+  for (int i = threadIdx.x; i < kSeedCols; i += kSeedThreads)
+    v[i] = i < n ? f32_to_ordered(dump[q * dump_ld + i]) : 0u;
+  for (int size = 2; size <= kSeedCols; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kSeedCols / 2; i += kSeedThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const uint32_t a = v[lo], b = v[hi];
+        if ((a < b) == desc) {
+          v[lo] = b;
+          v[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t kth = (k_sel <= n) ? v[k_sel - 1] : 0u;
+    thr_out[q] = kth > f32_to_ordered(-INFINITY) ? ordered_to_f32(kth) : -INFINITY;
   }
 }
 
@@ -891,31 +1014,72 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
   return PVDB_OK;
 }
 
+// Kernel variant for (element type, cluster size, pair MMA, pool size).
 template <bool BF16, int CL, bool PAIR>
-static int launch_batch_t(const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p, int grid,
-                          cudaStream_t st) {
-  auto run = [&](auto kern) -> int {
-    PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmem)));
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kBatchThreads);
-    cfg.dynamicSmemBytes = kBatchSmem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    PVDB_CUDA(cudaLaunchKernelEx(&cfg, kern, mq, mdb, p));
-    PVDB_LAUNCH_CHECK();
-    return PVDB_OK;
-  };
-  switch (p.pool_cap) {
-    case 128: return run(batch_topk_kernel<BF16, 4, CL, PAIR>);
-    default: return run(batch_topk_kernel<BF16, 8, CL, PAIR>);
+static const void* batch_kernel_ptr(int pool_cap) {
+  return pool_cap == 128 ? reinterpret_cast<const void*>(batch_topk_kernel<BF16, 4, CL, PAIR>)
+                         : reinterpret_cast<const void*>(batch_topk_kernel<BF16, 8, CL, PAIR>);
+}
+
+static const void* batch_kernel(bool bf16, int cl, bool pair, int pool_cap) {
+  if (pair) return bf16 ? batch_kernel_ptr<true, 2, true>(pool_cap) : batch_kernel_ptr<false, 2, true>(pool_cap);
+  switch (cl) {
+    case 8: return bf16 ? batch_kernel_ptr<true, 8, false>(pool_cap) : batch_kernel_ptr<false, 8, false>(pool_cap);
+    case 4: return bf16 ? batch_kernel_ptr<true, 4, false>(pool_cap) : batch_kernel_ptr<false, 4, false>(pool_cap);
+    case 2: return bf16 ? batch_kernel_ptr<true, 2, false>(pool_cap) : batch_kernel_ptr<false, 2, false>(pool_cap);
+    default: return bf16 ? batch_kernel_ptr<true, 1, false>(pool_cap) : batch_kernel_ptr<false, 1, false>(pool_cap);
   }
+}
+
+static void batch_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int cl, int grid, cudaStream_t st) {
+  cfg = cudaLaunchConfig_t{};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(kBatchThreads);
+  cfg.dynamicSmemBytes = kBatchSmem;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+}
+
+// How many clusters of `cl` CTAs of this kernel the device can hold at once (one CTA per SM; a
+// cluster must fit a GPC, so sizes above 2 may leave a few SMs unused).  The static visit schedule
+// needs every unit resident, so the grid never exceeds this.
+static int batch_max_units(const void* kern, int cl, int* out) {
+  static std::mutex mu;
+  static std::vector<std::pair<const void*, int>> cache;
+  std::lock_guard<std::mutex> g(mu);
+  for (auto& e : cache)
+    if (e.first == kern) {
+      *out = e.second;
+      return PVDB_OK;
+    }
+  PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmem)));
+  if (cl > 8) PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  batch_launch_config(cfg, attr, cl, cl * (kNumSMs / cl), nullptr);
+  int n = 0;
+  PVDB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+  if (n < 1) return fail(PVDB_ERR_CUDA, "batch: the device cannot hold one cluster of %d CTAs", cl);
+  n = std::min(n, kNumSMs / cl);
+  cache.emplace_back(kern, n);
+  *out = n;
+  return PVDB_OK;
+}
+
+static int launch_batch(const void* kern, int cl, const CUtensorMap& mq, const CUtensorMap& mdb, const BatchParams& p,
+                        int grid, cudaStream_t st) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  batch_launch_config(cfg, attr, cl, grid, st);
+  void* args[3] = {const_cast<CUtensorMap*>(&mq), const_cast<CUtensorMap*>(&mdb), const_cast<BatchParams*>(&p)};
+  PVDB_CUDA(cudaLaunchKernelExC(&cfg, kern, args));
+  PVDB_LAUNCH_CHECK();
+  return PVDB_OK;
 }
 
 int batch_max_k(bool use_bf16, bool rescore) { return kMaxSel - (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0); }
@@ -930,18 +1094,17 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   // Two query tiles or more: 2-CTA clusters share every database tile through TMA multicast (each
   // CTA fetches half of the tile's rows), which cuts the L2 -> shared-memory traffic per CTA from
   // 48 KB to 32 KB per K block.  A single query tile has nobody to share with.
-  const bool cluster_ok = getenv("PVDB_BATCH_NO_CLUSTER") == nullptr;
+  // Clusters of CL CTAs take CL consecutive query tiles of the same database tile; each CTA fetches
+  // 1/CL of the tile's rows and multicasts it.  L2 -> SM traffic per CTA and K block is 16 KB (its
+  // query slice) + 32/CL KB; the L2 delivers ~43 B/clk per SM, the tensor core consumes a K block in
+  // 512 clk (tf32) -- CL = 1: 94 B/clk needed, 2: 64, 4: 48, 8: 40.
+  int cl_max = getenv("PVDB_BATCH_NO_CLUSTER") ? 1 : kClusterDefault;
+  if (const char* e = getenv("PVDB_BATCH_CLUSTER")) cl_max = std::max(1, atoi(e));
   // cta_group::2 MMAs (one M=256 instruction per CTA pair); PVDB_BATCH_PAIR=0 keeps the multicast variant
   const char* pair_env = getenv("PVDB_BATCH_PAIR");
   const bool pair_mma = pair_env ? atoi(pair_env) != 0 : kPairDefault;
-  CUtensorMap mdb, mdb_half;
-  if (use_bf16) {
-    PVDB_TRY(encode_map(&mdb, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN));
-    PVDB_TRY(encode_map(&mdb_half, true, s->bf16.ptr, s->dim, s->capacity, s->ld_bf16, kBN / 2));
-  } else {
-    PVDB_TRY(encode_map(&mdb, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN));
-    PVDB_TRY(encode_map(&mdb_half, false, s->f32.ptr, s->dim, s->capacity, s->ld_f32, kBN / 2));
-  }
+  const void* db_ptr = use_bf16 ? s->bf16.ptr : s->f32.ptr;
+  const int db_ld = use_bf16 ? s->ld_bf16 : s->ld_f32;
 
   const int64_t max_q = static_cast<int64_t>(kMaxQTiles) * kBM;
   const int total_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
@@ -971,60 +1134,85 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     if (static_cast<int64_t>(sample_tiles) * p.q_tiles < min_sample_visits) sample_tiles = 0;
 
     const int grid_max = kNumSMs;  // pools / flags are sized for a full grid
-    const size_t pool_bytes = static_cast<size_t>(grid_max) * p.q_tiles * kBM * p.pool_cap * sizeof(uint64_t);
+    const size_t n_pools = static_cast<size_t>(grid_max) * p.q_tiles * kEpiHalves * kBM;
+    const size_t pool_bytes = n_pools * p.pool_cap * sizeof(uint64_t);
+    const size_t count_bytes = (n_pools * sizeof(uint16_t) + 255) & ~size_t(255);
     const size_t touched_bytes = (static_cast<size_t>(grid_max) * p.q_tiles + 255) & ~size_t(255);
     const size_t thr_bytes = (static_cast<size_t>(nq) * sizeof(uint32_t) + 255) & ~size_t(255);
     const size_t carry_bytes = sample_tiles ? ((static_cast<size_t>(nq) * k_sel * sizeof(uint64_t) + 255) & ~size_t(255)) : 0;
     const size_t init_bytes = sample_tiles ? thr_bytes : 0;
-    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes + carry_bytes + init_bytes));
+    // Seed pass: the first two tiles are multiplied once more with the scores written out; their
+    // k_sel-th best per query starts every threshold (see seed_threshold_kernel), which removes the
+    // cold start (every score of the first tiles appended, pools pruned over and over).
+    const bool seed = total_tiles >= 4 * kSeedTiles && getenv("PVDB_BATCH_NO_SEED") == nullptr;
+    const size_t seed_thr_bytes = seed ? thr_bytes : 0;
+    const size_t dump_bytes = seed ? static_cast<size_t>(p.q_tiles) * kBM * kSeedCols * sizeof(float) : 0;
+    PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes + carry_bytes + init_bytes + count_bytes +
+                              seed_thr_bytes + dump_bytes));
     unsigned char* base = static_cast<unsigned char*>(s->d_misc.ptr);
     p.pools = reinterpret_cast<uint64_t*>(base);
     p.touched = base + pool_bytes;
     p.shared_thr = reinterpret_cast<uint32_t*>(p.touched + touched_bytes);
     uint64_t* carry = reinterpret_cast<uint64_t*>(base + pool_bytes + touched_bytes + thr_bytes);
     float* init_thr = reinterpret_cast<float*>(base + pool_bytes + touched_bytes + thr_bytes + carry_bytes);
+    p.counts = reinterpret_cast<uint16_t*>(base + pool_bytes + touched_bytes + thr_bytes + carry_bytes + init_bytes);
+    float* seed_thr = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(p.counts) + count_bytes);
+    float* dump = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(seed_thr) + seed_thr_bytes);
 
     CUtensorMap mq;
     if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
     else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, s->dim, nq, s->ldq, kBM));
 
     auto run_pass = [&](int tile_begin, int n_tiles, const float* thr_in, const uint64_t* carry_in, uint64_t* carry_out,
-                        float* thr_out, bool pin_query_tiles) -> int {
+                        float* thr_out, bool pin_query_tiles, bool dump_scores = false) -> int {
       p.tile_begin = tile_begin;
       p.n_tiles = n_tiles;
       p.init_thr = thr_in;
-      const bool cluster = cluster_ok && p.q_tiles >= 2;
-      const int cl = cluster ? 2 : 1;
+      p.dump = dump_scores ? dump : nullptr;
+      p.dump_ld = kSeedCols;
+      // largest allowed cluster that does not pad the query tiles by more than a third
+      int cl = 1;
+      for (int c = 2; c <= cl_max && c <= 8; c <<= 1)
+        if (p.q_tiles >= c && ((p.q_tiles + c - 1) / c) * c * 3 <= p.q_tiles * 4) cl = c;
+      const bool pair = pair_mma && cl >= 2;
+      if (pair) cl = 2;
+      const void* kern = batch_kernel(use_bf16, cl, pair, p.pool_cap);
+      int max_units = 0;
+      PVDB_TRY(batch_max_units(kern, cl, &max_units));
+      CUtensorMap mdb;  // box = the rows one CTA fetches per K block
+      PVDB_TRY(encode_map(&mdb, use_bf16, db_ptr, s->dim, s->capacity, db_ld, kBN / cl));
       const int64_t n_visits = static_cast<int64_t>(n_tiles) * ((p.q_tiles + cl - 1) / cl);
-      const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, kNumSMs / cl));
+      const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, max_units));
       // pinned schedule: stride = (query-tile pairs) x (units per pair), so a unit never changes pair
       const int n_qp = (p.q_tiles + cl - 1) / cl, n_units = grid / cl;
       p.visit_stride = (pin_query_tiles && n_units >= n_qp) ? n_qp * (n_units / n_qp) : 0;
       PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
-      if (cluster && pair_mma) {
-        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2, true>(mq, mdb_half, p, grid, st)));
-        else PVDB_TRY((launch_batch_t<false, 2, true>(mq, mdb_half, p, grid, st)));
-      } else if (cluster) {
-        if (use_bf16) PVDB_TRY((launch_batch_t<true, 2, false>(mq, mdb_half, p, grid, st)));
-        else PVDB_TRY((launch_batch_t<false, 2, false>(mq, mdb_half, p, grid, st)));
-      } else {
-        if (use_bf16) PVDB_TRY((launch_batch_t<true, 1, false>(mq, mdb, p, grid, st)));
-        else PVDB_TRY((launch_batch_t<false, 1, false>(mq, mdb, p, grid, st)));
+      PVDB_TRY(launch_batch(kern, cl, mq, mdb, p, grid, st));
+      if (dump_scores) {
+        const int n = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(n_tiles) * kBN, s->rows - static_cast<int64_t>(tile_begin) * kBN));
+        seed_threshold_kernel<<<static_cast<unsigned>(nq), kSeedThreads, 0, st>>>(dump, kSeedCols, n, p.k_sel, thr_out);
+        PVDB_LAUNCH_CHECK();
+        return PVDB_OK;
       }
       finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
-          p.pools, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
+          p.pools, p.counts, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
           static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
-          d_out_rows + q0 * k, carry_in, carry_out, thr_out);
+          d_out_rows + q0 * k, carry_in, carry_out, thr_out, p.shared_thr, thr_in);
       PVDB_LAUNCH_CHECK();
       return PVDB_OK;
     };
+    const float* thr0 = nullptr;
+    if (seed) {
+      PVDB_TRY(run_pass(0, kSeedTiles, nullptr, nullptr, nullptr, seed_thr, false, true));
+      thr0 = seed_thr;
+    }
     if (sample_tiles > 0) {
-      PVDB_TRY(run_pass(0, sample_tiles, nullptr, nullptr, carry, init_thr, true));
+      PVDB_TRY(run_pass(0, sample_tiles, thr0, nullptr, carry, init_thr, true));
       PVDB_TRY(run_pass(sample_tiles, total_tiles - sample_tiles, init_thr, carry, nullptr, nullptr, false));
     } else {
-      // small problem, single pass: pinning each unit to one query tile (pair) keeps it to ONE cold
-      // start; the few surplus units that idle cost less than warming up several states per CTA
-      PVDB_TRY(run_pass(0, total_tiles, nullptr, nullptr, nullptr, nullptr, true));
+      // small problem, single pass: pinning each unit to one query tile (pair) keeps it to ONE
+      // threshold state; the few surplus units that idle cost less than several states per CTA
+      PVDB_TRY(run_pass(0, total_tiles, thr0, nullptr, nullptr, nullptr, true));
     }
   }
   return PVDB_OK;

@@ -39,7 +39,7 @@ def main():
         fn(buf, 16, 0)
         v = dict(zip(NAMES, [int(x) for x in buf[:11]]))
         launches = max(v["launches"], 1)
-        ew = 148 * 4  # epilogue warps per launch (upper bound: idle units count as zero time)
+        ew = 148 * 8  # epilogue warps per launch (upper bound: idle units count as zero time)
         out = {"config": spec, "ms": ms, "launches_in_sample": launches}
         for name in ("epi_loop_cyc", "epi_wait_tfull_cyc", "epi_prune_cyc", "epi_final_prune_cyc"):
             out[name + "_per_warp"] = v[name] / ew
