@@ -418,3 +418,31 @@ def test_batch_through_picovectordb(tmp_path):
     got = np.array([[r[K_ID] for r in rows] for rows in res])
     assert (got == ref_r).mean() >= 0.995
     db.close()
+
+
+@pytest.mark.parametrize("precision,mirror", [("tf32", False), ("bf16", True)])
+def test_batch_duplicate_rows_tie_order(store_factory, precision, mirror):
+    """Every vector is stored three times (rows r, r + n, r + 2n): scores tie exactly, so the result
+    must list the copies by ascending row and never lose the lowest copy at a selection boundary --
+    the two accumulator halves and the CTAs share thresholds, which must stay non-strict for this."""
+    n, dim, nq, k = 6000, 64, 200, 9
+    base = _gauss(n, dim, 77)
+    s = store_factory(dim, bf16_mirror=mirror)
+    s.upsert_range(np.concatenate([base, base, base]), 0)
+    q = _gauss(nq, dim, 78)
+    q[:5] = base[:5]
+    sc, rows = s.search(q, k, precision=precision)
+    store = s.download()
+    qn = O.prepare_queries(q, dim)[0]
+    exact = (store[:n] @ qn.T).T                                   # (nq, n) fp32 scores of the distinct vectors
+    best = np.argsort(-exact, axis=1, kind="stable")[:, : k // 3]
+    want = (best[:, :, None] + np.arange(3)[None, None, :] * n).reshape(nq, k)
+    if precision == "tf32":
+        np.testing.assert_array_equal(rows, want)
+    else:  # bf16 candidates, fp32 re-scored: near-ties between distinct vectors may swap
+        assert (rows == want).mean() > 0.97
+    trip = rows.reshape(nq, k // 3, 3)
+    assert (np.diff(trip, axis=2) == n).all()                      # copies in ascending row order
+    sc3 = sc.reshape(nq, k // 3, 3)
+    assert (sc3.max(axis=2) == sc3.min(axis=2)).all()              # and with identical scores
+    assert rows[:5, 0].tolist() == [0, 1, 2, 3, 4]
