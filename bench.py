@@ -240,7 +240,7 @@ def run_reference_arm(args, world, rank):
         "gpu_launches": 0,
         "host": {"cpu_count": os.cpu_count(), "blas_threads": threads, "wall_s": time.perf_counter() - t0},
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -273,7 +273,9 @@ def run_b200(args, world, rank, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout (one JSON line only)
+        # stdout carries exactly one JSON line: NCCL's version banner / warnings go to stderr
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     r0, r1 = shard_range(args.rows, world, rank)
@@ -319,6 +321,23 @@ def run_b200(args, world, rank, local_rank):
     sampler.start()
     for i in range(args.warmup):
         step_device(i)
+    barrier()
+    # nvidia-smi needs ~1 s before its first sample: when the whole timed region is shorter than that
+    # (sharded runs: a few ms per step), keep the GPUs under the same load with extra untimed steps --
+    # the same number on every rank, the steps contain a collective
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for i in range(3):
+        step_device(i)
+    pe1.record()
+    torch.cuda.synchronize()
+    probe = torch.tensor([pe0.elapsed_time(pe1) / 3.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+    step_ms = max(float(probe.item()), 1e-3)
+    if step_ms * args.steps < 1500.0:
+        for i in range(min(20000, int((1500.0 - step_ms * args.steps) / step_ms) + 1)):
+            step_device(i)
     barrier()
     launches0 = N.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -421,14 +440,37 @@ def run_b200(args, world, rank, local_rank):
             per_query, sample, _ = time_oracle(args, args.cpu_queries)
             line["cpu_baseline"] = {"value": 1.0 / per_query, "unit": UNIT, "cores": blas_threads(), "kind": "port",
                                     "sample": sample}
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     store.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit_json(line: dict) -> None:
+    """The one JSON line of the contract, written to the process's ORIGINAL stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_OUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_OUT, data)
+
+
+def _reserve_stdout() -> None:
+    """Keep stdout for the JSON line only: libraries that print to fd 1 (NCCL's version banner does,
+    whatever NCCL_DEBUG_FILE says) are pointed at stderr for the rest of the run."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     args = parse_args()
+    _reserve_stdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

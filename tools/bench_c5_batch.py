@@ -44,6 +44,7 @@ def main():
     dev = torch.device("cuda", lr)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     r0, r1 = shard_range(args.rows, world, rank)
     n_local = r1 - r0
