@@ -383,14 +383,18 @@ class PicoVectorDB:
             step = max(32, ((64 << 20) // (self.dim * 4)) // 32 * 32)
             for r0 in range(0, count, step):
                 r1 = min(count, r0 + step)
-                self._engine.upload(np.ascontiguousarray(vectors[r0:r1], dtype=Float), r0, active[r0:r1])
+                # the slice stays a lazy view of the mapped file: a sharded engine only reads its own rows
+                self._engine.upload(vectors[r0:r1], r0, active[r0:r1])
             logger.info("Loaded %d active / %d total vectors", len(self._id2idx), count)
         else:
             if self._capacity is not None:
                 cap = int(self._capacity)
                 self._ids = [None] * cap
                 self._docs = [None] * cap
-                self._free = list(range(cap))
+                # popped from the end, as in the reference; a row-sharded engine supplies an order that
+                # deals the rows out over its shards so a partly filled store is balanced
+                order = getattr(self._engine, "free_order", None)
+                self._free = order(cap) if order is not None else list(range(cap))
                 if self._use_memmap:
                     # keep the reference's observable side effect: a pre-sized raw file
                     np.memmap(vecs_file, dtype=Float, mode="w+", shape=(cap, self.dim)).flush()
@@ -422,22 +426,28 @@ class PicoVectorDB:
             tmp_vecs_base = f"{self._path}.vecs.tmp"
             tmp_vecs = f"{tmp_vecs_base}.npy"
             tmp_meta = f"{meta_file}.tmp"
+            # a row-sharded engine (sharded.ShardedStore): every rank makes this call, ONE rank writes
+            # the shared files, all ranks write their own rows of the matrix
+            writer = getattr(self._engine, "is_writer", True)
             try:
-                with open(tmp_ids, "w", encoding="utf-8") as f:
-                    json.dump(self._ids, f, ensure_ascii=False)
+                if writer:
+                    with open(tmp_ids, "w", encoding="utf-8") as f:
+                        json.dump(self._ids, f, ensure_ascii=False)
                 self._write_vectors(tmp_vecs)
-                with open(tmp_meta, "w", encoding="utf-8") as f:
-                    json.dump(
-                        {"embedding_dim": self.dim, "data": self._docs, "additional_data": self._additional},
-                        f,
-                        ensure_ascii=False,
-                    )
-                os.replace(tmp_ids, ids_file)
-                os.replace(tmp_vecs, vecs_file)
-                os.replace(tmp_meta, meta_file)
-                logger.info("Saved %d vectors", len(self._ids))
+                if writer:
+                    with open(tmp_meta, "w", encoding="utf-8") as f:
+                        json.dump(
+                            {"embedding_dim": self.dim, "data": self._docs, "additional_data": self._additional},
+                            f,
+                            ensure_ascii=False,
+                        )
+                    os.replace(tmp_ids, ids_file)
+                    os.replace(tmp_vecs, vecs_file)
+                    os.replace(tmp_meta, meta_file)
+                    logger.info("Saved %d vectors", len(self._ids))
+                self._engine_barrier()
             finally:
-                for tmp in (tmp_ids, tmp_vecs, tmp_meta):
+                for tmp in (tmp_ids, tmp_vecs, tmp_meta) if writer else ():
                     if os.path.exists(tmp):
                         try:
                             os.remove(tmp)
@@ -448,19 +458,35 @@ class PicoVectorDB:
         """Write the ``.npy`` file (same header as ``np.save``) in row blocks straight from the
         device, so saving never needs a second full copy of the matrix in host memory."""
         n = len(self._ids)
-        if n == 0 or self._host_cache is not None:
+        eng = self._engine
+        writer = getattr(eng, "is_writer", True)
+        sharded = hasattr(eng, "owned_rows")
+        if n == 0 or (self._host_cache is not None and not sharded):
             with open(path, "wb") as f:
                 np.save(f, self._vectors)
             return
         from numpy.lib.format import open_memmap
 
-        out = open_memmap(path, mode="w+", dtype=Float, shape=(n, self.dim))
+        # the writer creates the file (header + size); with a sharded engine the other ranks then map
+        # it and every rank stores the rows it owns
+        out = open_memmap(path, mode="w+", dtype=Float, shape=(n, self.dim)) if writer else None
+        self._engine_barrier()
+        if out is None:
+            out = open_memmap(path, mode="r+")
+        lo, hi = eng.owned_rows() if sharded else (0, n)
+        lo, hi = max(lo, 0), min(hi, n)
         step = max(1, (64 << 20) // (self.dim * 4))
-        for r0 in range(0, n, step):
-            r1 = min(n, r0 + step)
-            out[r0:r1] = self._engine.download(r0, r1 - r0)
+        for r0 in range(lo, hi, step):
+            r1 = min(hi, r0 + step)
+            out[r0:r1] = eng.download(r0, r1 - r0)
         out.flush()
         del out
+        self._engine_barrier()
+
+    def _engine_barrier(self) -> None:
+        barrier = getattr(self._engine, "barrier", None)
+        if barrier is not None:
+            barrier()
 
     def flush(self) -> None:
         """No-op: the store is device resident; ``save()`` writes the files."""

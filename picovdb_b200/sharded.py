@@ -170,3 +170,174 @@ class ShardedSearch:
     def _host_row_base(self) -> int:
         # a test engine that does not implement row_base itself gets the offset added here
         return 0 if getattr(self.local, "applies_row_base", False) else self.row0
+
+
+class ShardedStore:
+    """A store whose rows are split over the ranks of a process group, with ``DeviceStore``'s
+    interface -- so ``PicoVectorDB`` can sit on top of it unchanged (SPMD: every rank makes the same
+    calls with the same arguments and keeps the same ids / documents; only the vectors are sharded).
+
+    SURVEY.md 8(e): global row r lives on rank ``r // rows_per_rank`` (contiguous blocks, so a saved
+    matrix is the concatenation of the shards); upserts and deletes touch the owning shard only;
+    a search is every rank's local scan + one all-gather + the merge kernel (``ShardedSearch``).
+    The partition needs a fixed row capacity (``reserve_rows`` / PicoVectorDB's ``capacity=``).
+
+    ``local_factory`` / ``merge`` are test hooks (gloo process groups without GPUs).
+    """
+
+    def __init__(self, dim: int, device: Optional[int] = None, reserve_rows: int = 0, keep_f32: bool = True,
+                 bf16_mirror: bool = False, fixed_capacity: bool = False, *, group=None,
+                 local_factory: Optional[Callable] = None, merge: Optional[Callable] = None) -> None:
+        if reserve_rows <= 0:
+            raise ValueError("ShardedStore needs the total row capacity (reserve_rows / capacity=) to place rows")
+        self.dim = int(dim)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.capacity = int(reserve_rows)
+        self.row0, self.row1 = shard_range(self.capacity, self.world, self.rank)
+        self.per = shard_range(self.capacity, self.world, 0)[1]
+        if device is None:
+            device = int(torch.cuda.current_device()) if torch.cuda.is_available() else 0
+        if local_factory is None:
+            from .engine import DeviceStore as local_factory  # noqa: N813
+        self.local = local_factory(self.dim, device=device, reserve_rows=max(self.row1 - self.row0, 1),
+                                   keep_f32=keep_f32, bf16_mirror=bf16_mirror, fixed_capacity=fixed_capacity)
+        self._search = ShardedSearch(self.local, self.row0, group=group, merge=merge)
+        self._host_only = merge is not None
+        self._rows = 0  # global high-water mark (the same on every rank)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def rows(self) -> int:
+        return self._rows
+
+    @property
+    def is_writer(self) -> bool:
+        """True on the one rank that writes shared files (ids, documents, the .npy header)."""
+        return self.rank == 0
+
+    def owned_rows(self) -> tuple[int, int]:
+        return self.row0, self.row1
+
+    def free_order(self, cap: int) -> list[int]:
+        """Free-slot list for PicoVectorDB (it pops from the END): rows are handed out round-robin
+        over the shards -- shard 0's first row, shard 1's first row, ... -- so a store that is only
+        partly filled still spreads its rows (and the scan work) evenly."""
+        seq = [(j % self.world) * self.per + j // self.world for j in range(self.per * self.world)]
+        seq = [r for r in seq if r < cap]
+        return seq[::-1]
+
+    def barrier(self) -> None:
+        """Host-level barrier (used around shared files): an NCCL barrier is only stream ordered, so
+        the host also waits for it."""
+        if self.world > 1:
+            dist.barrier(group=self.group)
+            if not self._host_only and torch.cuda.is_available():
+                torch.cuda.synchronize()
+
+    def _sum_over_ranks(self, arr: np.ndarray) -> np.ndarray:
+        """Element-wise sum of a same-shaped array over the ranks (every rank gets the result)."""
+        if self.world == 1:
+            return arr
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if not self._host_only and torch.cuda.is_available():
+            t = t.cuda()
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def _mine(self, rows: np.ndarray) -> np.ndarray:
+        return (rows >= self.row0) & (rows < self.row1)
+
+    # ------------------------------------------------------------------ write side
+    def reserve(self, rows: int) -> None:
+        if rows > self.capacity:
+            raise ValueError(f"ShardedStore capacity is fixed at {self.capacity} rows")
+
+    def upsert_rows(self, vecs: np.ndarray, rows: np.ndarray) -> None:
+        rows = np.asarray(rows, dtype=np.int64)
+        if rows.size and (rows.min() < 0 or rows.max() >= self.capacity):
+            raise ValueError("row outside the sharded store's capacity")
+        m = self._mine(rows)
+        if m.any():
+            self.local.upsert_rows(np.asarray(vecs)[m], rows[m] - self.row0)
+        if rows.size:
+            self._rows = max(self._rows, int(rows.max()) + 1)
+
+    def upsert_range(self, vecs: np.ndarray, row0: int) -> None:
+        n = len(vecs)
+        if row0 < 0 or row0 + n > self.capacity:
+            raise ValueError("row range outside the sharded store's capacity")
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1)
+        if hi > lo:
+            self.local.upsert_range(np.asarray(vecs)[lo - row0: hi - row0], lo - self.row0)
+        self._rows = max(self._rows, row0 + n)
+
+    def delete_rows(self, rows: np.ndarray) -> None:
+        rows = np.asarray(rows, dtype=np.int64)
+        m = self._mine(rows)
+        if m.any():
+            self.local.delete_rows(rows[m] - self.row0)
+
+    def upload(self, vecs: np.ndarray, row0: int = 0, active: Optional[np.ndarray] = None) -> None:
+        """Raw load of already-normalised rows [row0, row0 + len(vecs)); each rank keeps its part."""
+        n = len(vecs)
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1)
+        if hi > lo:
+            a = None if active is None else np.asarray(active, dtype=bool)[lo - row0: hi - row0]
+            self.local.upload(np.ascontiguousarray(vecs[lo - row0: hi - row0], dtype=np.float32), lo - self.row0, a)
+        self._rows = max(self._rows, row0 + n)
+
+    def compact(self, keep_rows: np.ndarray) -> None:
+        """Global compaction: new row j <- old row keep[j] (keep ascending, so keep[j] >= j and moving
+        block by block in ascending order never overwrites a row that is still to be read)."""
+        keep = np.asarray(keep_rows, dtype=np.int64)
+        step = max(32, ((32 << 20) // (self.dim * 4)) // 32 * 32)
+        for a in range(0, keep.size, step):
+            b = min(keep.size, a + step)
+            self.upload(self.fetch_rows(keep[a:b]), a, np.ones(b - a, dtype=bool))
+        n_local = int(np.clip(keep.size - self.row0, 0, self.row1 - self.row0))
+        self.local.compact(np.arange(n_local, dtype=np.int64))  # drops the shard's rows past the new end
+        self._rows = int(keep.size)
+
+    # ------------------------------------------------------------------ read side
+    def fetch_rows(self, rows: np.ndarray) -> np.ndarray:
+        rows = np.asarray(rows, dtype=np.int64)
+        out = np.zeros((rows.size, self.dim), dtype=np.float32)
+        m = self._mine(rows) & (rows - self.row0 < self.local.rows)  # rows never written read as zeros
+        if m.any():
+            out[m] = self.local.fetch_rows(rows[m] - self.row0)
+        return self._sum_over_ranks(out)
+
+    def download(self, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self._rows - row0
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1)
+        out = np.zeros((n, self.dim), dtype=np.float32)
+        used = min(hi, self.row0 + self.local.rows)  # the shard's rows past its high-water mark are zeros
+        if used > lo:
+            out[lo - row0: used - row0] = self.local.download(lo - self.row0, used - lo)
+        if lo == row0 and hi == row0 + n:
+            return out  # entirely this rank's rows: no collective
+        return self._sum_over_ranks(out)
+
+    def active_mask(self) -> np.ndarray:
+        out = np.zeros(self._rows, dtype=np.int32)
+        hi = min(self._rows, self.row1)
+        if hi > self.row0:
+            out[self.row0: hi] = np.asarray(self.local.active_mask(), dtype=bool)[: hi - self.row0]
+        return self._sum_over_ranks(out).astype(bool)
+
+    def search(self, queries: np.ndarray, k: int, prefilter: Optional[np.ndarray] = None, precision: str = "auto",
+               normalized: bool = False, **_) -> tuple[np.ndarray, np.ndarray]:
+        """``prefilter`` is the GLOBAL row mask (length >= rows); each rank applies its slice."""
+        pf = None
+        if prefilter is not None:
+            pf = np.zeros(max(self.row1 - self.row0, 0), dtype=bool)
+            hi = min(len(prefilter), self.row1)
+            if hi > self.row0:
+                pf[: hi - self.row0] = np.asarray(prefilter, dtype=bool)[self.row0: hi]
+        return self._search.search(queries, k, prefilter=pf, precision=precision)
+
+    def close(self) -> None:
+        self.local.close()

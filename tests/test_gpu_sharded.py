@@ -65,3 +65,83 @@ def test_sharded_search_nccl(tmp_path):
     )
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"SHARDED_OK {world}" in out.stdout
+
+
+DB_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PVDB_ROOT"])
+from oracle import picovdb_oracle as O
+from picovdb_b200 import K_ID, K_VECTOR, PicoVectorDB
+from picovdb_b200.sharded import ShardedStore, shard_range
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+
+class ShardedDB(PicoVectorDB):
+    _engine_factory = staticmethod(lambda dim, **kw: ShardedStore(dim, **kw))
+
+path = os.path.join(os.environ["PVDB_TMP"], "db")
+n, dim = 5000, 64
+rng = np.random.default_rng(11)
+vecs = rng.standard_normal((n, dim)).astype(np.float32)
+db = ShardedDB(embedding_dim=dim, storage_file=path, capacity=8192, no_faiss=True, device=lr)
+db.upsert([{K_VECTOR: vecs[i], K_ID: f"r{i}", "cat": i % 5} for i in range(n)])
+where = dict(db._id2idx)                      # id -> global row (dealt out over the shards)
+dead = [f"r{i}" for i in range(0, n, 9)]
+db.delete(dead)
+q = rng.standard_normal((6, dim)).astype(np.float32)
+res = db.query(q, top_k=8)
+res_w = db.query(q, top_k=8, where={"cat": 2})
+one = db.query(q[0], top_k=8)
+got_vec = db.get(["r1"], include_vector=True)[0][K_VECTOR]
+db.save()
+db.close()
+db2 = ShardedDB(embedding_dim=dim, storage_file=path, capacity=8192, no_faiss=True, device=lr)
+res2 = db2.query(q, top_k=8)
+db2.close()
+if rank == 0:
+    store = O.normalize_rows(vecs)
+    alive = np.ones(n, bool); alive[::9] = False
+    qn, _ = O.prepare_queries(q, dim)
+    ref_s, ref_r = O.search(store, qn, 8, alive)
+    ids = lambda rs: [[r[K_ID] for r in lst] for lst in rs]
+    want = [[f"r{j}" for j in row] for row in ref_r]
+    assert ids(res) == want and ids(res2) == want and [r[K_ID] for r in one] == want[0]
+    ref_s2, ref_r2 = O.search(store, qn, 8 + 32, alive, (np.arange(n) % 5) == 2)
+    assert ids(res_w) == [[f"r{j}" for j in row[:8]] for row in ref_r2]
+    np.testing.assert_allclose(got_vec, store[1], rtol=1e-6, atol=1e-7)
+    saved = np.load(path + ".vecs.npy")
+    assert saved.shape == (8192, dim)
+    np.testing.assert_allclose(saved[where["r1"]], store[1], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(saved[where["r4999"]], store[4999], rtol=1e-6, atol=1e-7)
+    assert not saved[where["r0"]].any() and not saved[where["r9"]].any()   # deleted rows are zero-filled, as in the reference
+    r0_, r1_ = shard_range(8192, world, 0)
+    on0 = sum(1 for r in where.values() if r < r1_)
+    assert abs(on0 - n // world) <= 1                                        # rows are dealt out evenly
+    print("SHARDED_DB_OK", world)
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_db_nccl(tmp_path):
+    """The drop-in class over a row-sharded store (ShardedStore): SPMD calls on every rank."""
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2
+    script = tmp_path / "db_worker.py"
+    script.write_text(DB_WORKER)
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    env = dict(os.environ, PVDB_ROOT=ROOT, PVDB_TMP=str(tmp_path))
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+        capture_output=True, text=True, timeout=600, env=env,
+    )
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert f"SHARDED_DB_OK {world}" in out.stdout
