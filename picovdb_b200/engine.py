@@ -208,6 +208,7 @@ class DeviceStore:
     MAX_COLUMNS = 16
 
     MAX_COLUMNS = 16  # pvdb_store::kMaxColumns
+    applies_row_base = True  # result rows already include set_row_base()'s offset
 
     def column_write(self, column: int, codes: np.ndarray, rows: Optional[np.ndarray] = None, row0: int = 0) -> None:
         """codes[i] (int32 >= 0, -1 = absent) for rows[i], or for the consecutive rows from row0."""

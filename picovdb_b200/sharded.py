@@ -137,7 +137,44 @@ class ShardedSearch:
             raise RuntimeError("ShardedSearch needs CUDA (no CPU compute path)")
         s_loc, r_loc = self.local.search(q, k, prefilter, precision=precision)
         r_loc = np.where(r_loc >= 0, r_loc + self._host_row_base(), r_loc)
-        nq = q.shape[0]
+        return self.merge_local(s_loc, r_loc, k)
+
+    def merge_local(self, s_loc: np.ndarray, r_loc: np.ndarray, k: int) -> tuple[np.ndarray, np.ndarray]:
+        """All-gather + merge of per-rank results that are already on the host (rows global, -1 padded):
+        the exchange step for searches that return through a host call (``search_where``)."""
+        nq = s_loc.shape[0]
+        n_out = nq * k
+        if self._host_merge is None and torch.cuda.is_available():
+            from .engine import merge_topk_dev
+
+            dev = torch.device("cuda", torch.cuda.current_device())
+            b = self._buffers(nq, k, dev)
+            key = ("merge", nq, k)
+            st = self._bufs.get(key)
+            if st is None:
+                st = {"hloc": torch.empty(packed_result_bytes(nq, k), dtype=torch.uint8).pin_memory(),
+                      "hout": torch.empty(packed_result_bytes(nq, k), dtype=torch.uint8).pin_memory()}
+                self._bufs[key] = st
+            raw = st["hloc"].numpy()
+            raw[: n_out * 8] = np.ascontiguousarray(r_loc, dtype="<i8").view(np.uint8).ravel()
+            raw[n_out * 8: n_out * 12] = np.ascontiguousarray(s_loc, dtype="<f4").view(np.uint8).ravel()
+            b["local"].copy_(st["hloc"], non_blocking=True)
+            if self.world == 1:
+                gathered = b["local"]
+            else:
+                dist.all_gather_into_tensor(b["all"], b["local"], group=self.group)
+                gathered = b["all"]
+            block = packed_result_bytes(nq, k)
+            merge_topk_dev(dev.index or 0, gathered.data_ptr() + n_out * 8, gathered.data_ptr(), self.world, nq, k,
+                           b["scores"].data_ptr(), b["rows"].data_ptr(), stream=torch.cuda.current_stream().cuda_stream,
+                           scores_stride=block // 4, rows_stride=block // 8)
+            st["hout"].copy_(b["out"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            out = st["hout"].numpy()
+            return (out[n_out * 8: n_out * 12].view("<f4").reshape(nq, k).copy(),
+                    out[: n_out * 8].view("<i8").reshape(nq, k).copy())
+        if self._host_merge is None:
+            raise RuntimeError("ShardedSearch needs CUDA (no CPU compute path)")
         packed = np.zeros(packed_result_bytes(nq, k), dtype=np.uint8)
         packed[: nq * k * 8] = r_loc.astype("<i8").view(np.uint8).ravel()
         packed[nq * k * 8 : nq * k * 12] = s_loc.astype("<f4").view(np.uint8).ravel()
@@ -148,7 +185,6 @@ class ShardedSearch:
             gathered = torch.empty(self.world * loc.numel(), dtype=torch.uint8)
             dist.all_gather_into_tensor(gathered, loc, group=self.group)
         blocks = gathered.numpy().reshape(self.world, -1)
-        n_out = nq * k
         rows = [blk[: n_out * 8].view("<i8").reshape(nq, k) for blk in blocks]
         scores = [blk[n_out * 8 : n_out * 12].view("<f4").reshape(nq, k) for blk in blocks]
         return self._host_merge(scores, rows, k)
@@ -206,6 +242,7 @@ class ShardedStore:
         self._search = ShardedSearch(self.local, self.row0, group=group, merge=merge)
         self._host_only = merge is not None
         self._rows = 0  # global high-water mark (the same on every rank)
+        self._cols: set[int] = set()  # metadata columns this rank holds codes for
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -298,6 +335,7 @@ class ShardedStore:
             self.upload(self.fetch_rows(keep[a:b]), a, np.ones(b - a, dtype=bool))
         n_local = int(np.clip(keep.size - self.row0, 0, self.row1 - self.row0))
         self.local.compact(np.arange(n_local, dtype=np.int64))  # drops the shard's rows past the new end
+        self._cols.clear()                                      # ... and its metadata columns
         self._rows = int(keep.size)
 
     # ------------------------------------------------------------------ read side
@@ -338,6 +376,54 @@ class ShardedStore:
             if hi > self.row0:
                 pf[: hi - self.row0] = np.asarray(prefilter, dtype=bool)[self.row0: hi]
         return self._search.search(queries, k, prefilter=pf, precision=precision)
+
+    # ------------------------------------------------------------------ metadata columns / dict filters
+    MAX_COLUMNS = 16
+
+    def column_write(self, column: int, codes: np.ndarray, rows: Optional[np.ndarray] = None, row0: int = 0) -> None:
+        """Codes of the given global rows (or of the consecutive rows from row0); each rank keeps the
+        codes of the rows it owns."""
+        codes = np.asarray(codes, dtype=np.int32)
+        if rows is not None:
+            rows = np.asarray(rows, dtype=np.int64)
+            m = self._mine(rows) & (rows - self.row0 < self.local.rows)
+            if m.any():
+                self.local.column_write(column, codes[m], rows=rows[m] - self.row0)
+                self._cols.add(column)
+            return
+        lo, hi = max(row0, self.row0), min(row0 + codes.size, self.row0 + self.local.rows)
+        if hi > lo:
+            self.local.column_write(column, codes[lo - row0: hi - row0], row0=lo - self.row0)
+            self._cols.add(column)
+
+    def column_drop(self, column: int) -> None:
+        if column in self._cols:
+            self.local.column_drop(column)
+            self._cols.discard(column)
+
+    def search_where(self, queries: np.ndarray, k: int, column: int, wanted_codes, extra: Optional[np.ndarray] = None,
+                     precision: str = "auto") -> tuple[np.ndarray, np.ndarray, int]:
+        """Every rank filters and scans its own rows on its GPU; results are merged as in ``search`` and
+        the candidate counts are summed.  ``extra`` is the GLOBAL row mask of an ``ids=`` restriction."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = q.shape[0]
+        if column in self._cols and self.local.rows > 0:
+            ex = None
+            if extra is not None:
+                ex = np.zeros(self.local.rows, dtype=bool)
+                hi = min(len(extra), self.row0 + self.local.rows)
+                if hi > self.row0:
+                    ex[: hi - self.row0] = np.asarray(extra, dtype=bool)[self.row0: hi]
+            s_loc, r_loc, cand = self.local.search_where(q, k, column, wanted_codes, ex, precision=precision)
+            if not getattr(self.local, "applies_row_base", False):
+                r_loc = np.where(r_loc >= 0, r_loc + self.row0, r_loc)
+        else:  # this rank holds no row of the column
+            s_loc = np.full((nq, k), -np.inf, dtype=np.float32)
+            r_loc = np.full((nq, k), -1, dtype=np.int64)
+            cand = 0
+        scores, rows = self._search.merge_local(s_loc, r_loc, k)
+        total = int(self._sum_over_ranks(np.array([cand], dtype=np.int64))[0])
+        return scores, rows, total
 
     def close(self) -> None:
         self.local.close()

@@ -92,7 +92,10 @@ dead = [f"r{i}" for i in range(0, n, 9)]
 db.delete(dead)
 q = rng.standard_normal((6, dim)).astype(np.float32)
 res = db.query(q, top_k=8)
-res_w = db.query(q, top_k=8, where={"cat": 2})
+res_w = db.query(q, top_k=8, where={"cat": 2})            # evaluated on every shard's GPU (search_where)
+some = [f"r{i}" for i in range(0, n, 3)]
+res_wi = db.query(q, top_k=8, where={"cat": {"$in": [1, 4]}}, ids=some)
+k_eff_wi = db._last_k_eff
 one = db.query(q[0], top_k=8)
 got_vec = db.get(["r1"], include_vector=True)[0][K_VECTOR]
 db.save()
@@ -110,6 +113,10 @@ if rank == 0:
     assert ids(res) == want and ids(res2) == want and [r[K_ID] for r in one] == want[0]
     ref_s2, ref_r2 = O.search(store, qn, 8 + 32, alive, (np.arange(n) % 5) == 2)
     assert ids(res_w) == [[f"r{j}" for j in row[:8]] for row in ref_r2]
+    pf = np.isin(np.arange(n) % 5, [1, 4]) & (np.arange(n) % 3 == 0)
+    ref_s3, ref_r3 = O.search(store, qn, 8 + 32, alive, pf)
+    assert ids(res_wi) == [[f"r{j}" for j in row[:8]] for row in ref_r3]
+    assert k_eff_wi == min(40, int((pf & alive).sum()))
     np.testing.assert_allclose(got_vec, store[1], rtol=1e-6, atol=1e-7)
     saved = np.load(path + ".vecs.npy")
     assert saved.shape == (8192, dim)

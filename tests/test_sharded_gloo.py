@@ -98,6 +98,10 @@ def _db_script(db, rng, out):
     ids = lambda res: [[r[K_ID] for r in lst] for lst in res]  # noqa: E731
     out["plain"] = ids(db.query(q, top_k=7))
     out["where"] = ids(db.query(q, top_k=5, where={"cat": 1}))
+    out["where_in"] = ids(db.query(q, top_k=400, where={"cat": {"$in": [0, 3]}}))     # more than there are candidates
+    out["where_ids"] = ids(db.query(q, top_k=4, where={"cat": 2}, ids=[f"r{i}" for i in range(0, 300, 2)]))
+    out["where_none"] = db.query(q, top_k=4, where={"cat": 99})
+    out["k_eff"] = db._last_k_eff
     out["callable"] = ids(db.query(q, top_k=5, where=lambda d: d["cat"] >= 2))
     out["ids"] = ids(db.query(q, top_k=3, ids=[f"r{i}" for i in range(100, 160)]))
     out["get"] = [np.round(r[K_VECTOR], 6).tolist() for r in db.get(["r5", "n3"], include_vector=True)]
@@ -131,6 +135,7 @@ def _db_worker(rank: int, world: int, port: int, out_dir: str) -> None:
         q = _db_script(db, np.random.default_rng(7), out)
         # vectors really are split: a rank only holds rows of its own block
         assert db._engine.local.rows <= db._engine.row1 - db._engine.row0
+        assert "search_where" in db._engine.local.calls          # dict filters ran on the shards
         db.close()
         # reload from the files all ranks just wrote together; each rank uploads only its rows
         db2 = ShardedDB(embedding_dim=16, storage_file=path, capacity=512, no_faiss=True)
