@@ -895,6 +895,7 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
     }
     __syncthreads();
     n_keys = s_n;
+    __syncthreads();  // nobody appends again (next round) before everyone has read the count
     c += take;
   }
   block_sort_prefix(keys, n_keys);
@@ -943,38 +944,67 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
 
 // ---------------------------------------------------------------------------- seed thresholds
 // One block per query: the k_sel-th largest of the query's `n` dumped scores (masked ones are -inf) is
-// a proven lower bound of its final k_sel-th best tensor-core score -- the main pass starts from it
-// instead of -inf.  n <= kSeedCols, sorted descending in shared memory.
-constexpr int kSeedTiles = 2;
-constexpr int kSeedCols = kSeedTiles * kBN;
-constexpr int kSeedThreads = 128;
+// a proven lower bound of its final k_sel-th best tensor-core score -- the selection passes start from
+// it instead of -inf.  Radix select over the order-preserving 32-bit image of the scores: four 8-bit
+// passes over a shared-memory copy, each narrowing the prefix of the k-th largest value.
+constexpr int kSeedTilesMax = 64;
+constexpr int kSeedColsMax = kSeedTilesMax * kBN;  // 16384 scores = 64 KB of (dynamic) shared memory
+constexpr int kSeedThreads = 256;
 
 __global__ void __launch_bounds__(kSeedThreads)
 seed_threshold_kernel(const float* __restrict__ dump, int dump_ld, int n, int k_sel, float* __restrict__ thr_out) {
-  __shared__ uint32_t v[kSeedCols];
+  extern __shared__ uint32_t v[];  // n scores
+  __shared__ unsigned hist[256];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_k;
   const int64_t q = blockIdx.x;
-  for (int i = threadIdx.x; i < kSeedCols; i += kSeedThreads)
-    v[i] = i < n ? f32_to_ordered(dump[q * dump_ld + i]) : 0u;
-  for (int size = 2; size <= kSeedCols; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < kSeedCols / 2; i += kSeedThreads) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool desc = (lo & size) == 0;
-        const uint32_t a = v[lo], b = v[hi];
-        if ((a < b) == desc) {
-          v[lo] = b;
-          v[hi] = a;
+  const int lane = threadIdx.x & 31;
+  if (n < k_sel) {
+    if (threadIdx.x == 0) thr_out[q] = -INFINITY;
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += kSeedThreads) v[i] = f32_to_ordered(dump[q * dump_ld + i]);
+  uint32_t prefix = 0u, mask = 0u;
+  int kk = k_sel;  // rank (1 = largest) of the wanted value among those that match the prefix
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0u;  // kSeedThreads == 256 bins
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSeedThreads) {
+      const uint32_t x = v[i];
+      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns bins 255 - 8l ... 248 - 8l (descending); find the bin holding the kk-th largest
+      unsigned mine = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mine += hist[255 - 8 * lane - j];
+      unsigned incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, incl >= static_cast<unsigned>(kk));
+      const int owner = __ffs(hit) - 1;  // n >= k_sel guarantees a hit
+      if (lane == owner) {
+        unsigned cum = incl - mine;
+        int bin = 255 - 8 * lane;
+        for (int j = 0; j < 8; ++j, --bin) {
+          const unsigned h = hist[bin];
+          if (cum + h >= static_cast<unsigned>(kk)) break;
+          cum += h;
         }
+        s_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
+        s_k = kk - static_cast<int>(cum);
       }
     }
+    __syncthreads();
+    prefix = s_prefix;
+    kk = s_k;
+    mask |= 255u << shift;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t kth = (k_sel <= n) ? v[k_sel - 1] : 0u;
-    thr_out[q] = kth > f32_to_ordered(-INFINITY) ? ordered_to_f32(kth) : -INFINITY;
-  }
+  if (threadIdx.x == 0) thr_out[q] = prefix > f32_to_ordered(-INFINITY) ? ordered_to_f32(prefix) : -INFINITY;
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -1141,12 +1171,16 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     const size_t thr_bytes = (static_cast<size_t>(nq) * sizeof(uint32_t) + 255) & ~size_t(255);
     const size_t carry_bytes = sample_tiles ? ((static_cast<size_t>(nq) * k_sel * sizeof(uint64_t) + 255) & ~size_t(255)) : 0;
     const size_t init_bytes = sample_tiles ? thr_bytes : 0;
-    // Seed pass: the first two tiles are multiplied once more with the scores written out; their
-    // k_sel-th best per query starts every threshold (see seed_threshold_kernel), which removes the
-    // cold start (every score of the first tiles appended, pools pruned over and over).
-    const bool seed = total_tiles >= 4 * kSeedTiles && getenv("PVDB_BATCH_NO_SEED") == nullptr;
+    // Seed pass: the first tiles (up to 8192 rows) are multiplied once more with the scores written
+    // out -- a plain GEMM, no selection -- and their k_sel-th best per query starts every threshold
+    // (seed_threshold_kernel).  That removes the cold start (every score of the first tiles appended,
+    // pools pruned over and over): the selection passes begin at a pass rate of k_sel / seed rows.
+    int seed_tiles = std::min(32, total_tiles / 8);  // these tiles are multiplied twice (<= 1/8 of a small store)
+    if (const char* e = getenv("PVDB_BATCH_SEED_TILES")) seed_tiles = std::min(kSeedTilesMax, atoi(e));
+    const bool seed = seed_tiles >= 2 && getenv("PVDB_BATCH_NO_SEED") == nullptr;
+    const int seed_cols = seed_tiles * kBN;
     const size_t seed_thr_bytes = seed ? thr_bytes : 0;
-    const size_t dump_bytes = seed ? static_cast<size_t>(p.q_tiles) * kBM * kSeedCols * sizeof(float) : 0;
+    const size_t dump_bytes = seed ? static_cast<size_t>(p.q_tiles) * kBM * seed_cols * sizeof(float) : 0;
     PVDB_TRY(s->d_misc.ensure(pool_bytes + touched_bytes + thr_bytes + carry_bytes + init_bytes + count_bytes +
                               seed_thr_bytes + dump_bytes));
     unsigned char* base = static_cast<unsigned char*>(s->d_misc.ptr);
@@ -1169,7 +1203,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       p.n_tiles = n_tiles;
       p.init_thr = thr_in;
       p.dump = dump_scores ? dump : nullptr;
-      p.dump_ld = kSeedCols;
+      p.dump_ld = seed_cols;
       // largest allowed cluster that does not pad the query tiles by more than a third
       int cl = 1;
       for (int c = 2; c <= cl_max && c <= 8; c <<= 1)
@@ -1190,7 +1224,12 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       PVDB_TRY(launch_batch(kern, cl, mq, mdb, p, grid, st));
       if (dump_scores) {
         const int n = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(n_tiles) * kBN, s->rows - static_cast<int64_t>(tile_begin) * kBN));
-        seed_threshold_kernel<<<static_cast<unsigned>(nq), kSeedThreads, 0, st>>>(dump, kSeedCols, n, p.k_sel, thr_out);
+        const size_t seed_smem = static_cast<size_t>(seed_cols) * sizeof(uint32_t);
+        if (seed_smem > 48 * 1024)
+          PVDB_CUDA(cudaFuncSetAttribute(seed_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(kSeedColsMax * sizeof(uint32_t))));
+        seed_threshold_kernel<<<static_cast<unsigned>(nq), kSeedThreads, seed_smem, st>>>(dump, seed_cols, n, p.k_sel,
+                                                                                          thr_out);
         PVDB_LAUNCH_CHECK();
         return PVDB_OK;
       }
@@ -1203,7 +1242,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     };
     const float* thr0 = nullptr;
     if (seed) {
-      PVDB_TRY(run_pass(0, kSeedTiles, nullptr, nullptr, nullptr, seed_thr, false, true));
+      PVDB_TRY(run_pass(0, seed_tiles, nullptr, nullptr, nullptr, seed_thr, false, true));
       thr0 = seed_thr;
     }
     if (sample_tiles > 0) {
