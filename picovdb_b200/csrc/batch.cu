@@ -791,6 +791,36 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------- radix select helper
+// hist[256] counts values per 8-bit digit; called by ONE full warp.  Finds the digit (bin) that
+// holds the kk-th largest value (bins are scanned from 255 down) and the rank of that value inside
+// the bin.  Requires sum(hist) >= kk.
+__device__ __forceinline__ void warp_find_bin_desc(const unsigned* hist, int kk, int lane, int& bin_out, int& rank_out) {
+  // lane l owns bins 255 - 8l ... 248 - 8l
+  unsigned mine = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine += hist[255 - 8 * lane - j];
+  unsigned incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const unsigned hit = __ballot_sync(0xffffffffu, incl >= static_cast<unsigned>(kk));
+  const int owner = __ffs(hit) - 1;
+  int bin = 255 - 8 * lane;
+  unsigned cum = incl - mine;
+  if (lane == owner) {
+    for (int j = 0; j < 8; ++j, --bin) {
+      const unsigned h = hist[bin];
+      if (cum + h >= static_cast<unsigned>(kk)) break;
+      cum += h;
+    }
+  }
+  bin_out = __shfl_sync(0xffffffffu, bin, owner);
+  rank_out = kk - static_cast<int>(__shfl_sync(0xffffffffu, cum, owner));
+}
+
 // ---------------------------------------------------------------------------- finalize
 // One block per query.  The candidate pools of every (CTA, half) that met the query's tile are
 // streamed through a filter -- a key survives if its score reaches the best lower bound known for the
@@ -829,6 +859,59 @@ __device__ __forceinline__ void block_sort_prefix(uint64_t* keys, int n) {
   block_sort_desc(keys, n_pow2);
 }
 
+// Keep the best `k_sel` of keys[0..n) (n <= kFinalCap, n > k_sel): radix select (four 8-bit passes over
+// the order-preserving score word, shared-memory histogram) finds the score of the k_sel-th best key,
+// then every key with at least that score is compacted to the front (unsorted).  Ties on the score
+// word are all kept, so the returned count can exceed k_sel by the number of ties; the caller falls
+// back to a full sort when that number is large.  Returns the new count; *bound = that score word.
+__device__ __forceinline__ int block_select_top(uint64_t* keys, int n, int k_sel, unsigned* hist, uint32_t* s_word,
+                                                int* s_int, uint32_t* bound) {
+  static_assert(kFinalThreads == 256, "one histogram bin per thread");
+  static_assert(kFinalCap % kFinalThreads == 0, "keys are held in registers during compaction");
+  const int lane = threadIdx.x & 31;
+  uint32_t prefix = 0u, mask = 0u;
+  int kk = k_sel;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kFinalThreads) {
+      const uint32_t x = static_cast<uint32_t>(keys[i] >> 32);
+      if ((x & mask) == prefix) atomicAdd(&hist[(x >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int bin, rank;
+      warp_find_bin_desc(hist, kk, lane, bin, rank);
+      if (lane == 0) {
+        *s_word = prefix | (static_cast<uint32_t>(bin) << shift);
+        *s_int = rank;
+      }
+    }
+    __syncthreads();
+    prefix = *s_word;
+    kk = *s_int;
+    mask |= 255u << shift;
+  }
+  // compaction: everybody reads its keys first, then the survivors are re-packed from slot 0
+  constexpr int kPer = kFinalCap / kFinalThreads;
+  uint64_t mine[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + j * kFinalThreads;
+    mine[j] = (i < n) ? keys[i] : 0ull;
+  }
+  if (threadIdx.x == 0) *s_int = 0;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPer; ++j)
+    if (mine[j] != 0ull && static_cast<uint32_t>(mine[j] >> 32) >= prefix) keys[atomicAdd(s_int, 1)] = mine[j];
+  __syncthreads();
+  *bound = prefix;
+  const int kept = *s_int;
+  __syncthreads();  // s_int is reused by the caller
+  return kept;
+}
+
 __global__ void __launch_bounds__(kFinalThreads)
 finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __restrict__ counts,
                       const uint8_t* __restrict__ touched, int n_ctas, int pool_cap, int k_sel, int q_tiles,
@@ -841,6 +924,9 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
   __shared__ int s_lists[kNumSMs];
   __shared__ int s_nlists;
   __shared__ int s_n;
+  __shared__ unsigned s_hist[256];
+  __shared__ uint32_t s_word;
+  __shared__ int s_int;
   const int64_t q = blockIdx.x;
   const int qt = static_cast<int>(q / kBM);
   const int ql = static_cast<int>(q % kBM);
@@ -869,27 +955,42 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
   if (threadIdx.x == 0) s_n = n_keys;
   __syncthreads();
   const int n_pools = s_nlists * kEpiHalves;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Cut the buffer to the best k_sel keys and raise the bound (cheap select; a full sort only when a
+  // crowd of keys ties on the score word, e.g. many copies of one vector).
+  auto cut = [&]() {
+    if (n_keys > k_sel) {
+      uint32_t bound;
+      int kept_now = block_select_top(keys, n_keys, k_sel, s_hist, &s_word, &s_int, &bound);
+      if (kept_now > k_sel + 64) {
+        block_sort_prefix(keys, kept_now);
+        kept_now = k_sel;
+        bound = static_cast<uint32_t>(keys[k_sel - 1] >> 32);
+        __syncthreads();
+      }
+      n_keys = kept_now;
+      lb = max(lb, bound);
+    }
+    if (threadIdx.x == 0) s_n = n_keys;
+    __syncthreads();
+  };
   int c = 0;
   while (c < n_pools) {
     // every pool taken this round may contribute up to pool_cap keys
     const int take = min(n_pools - c, (kFinalCap - n_keys) / pool_cap);
     if (take == 0) {
-      // buffer (nearly) full: sort, keep the best k_sel, tighten the bound
-      block_sort_prefix(keys, n_keys);
-      n_keys = min(n_keys, k_sel);
-      if (n_keys == k_sel && keys[k_sel - 1] != 0ull) lb = max(lb, static_cast<uint32_t>(keys[k_sel - 1] >> 32));
-      __syncthreads();
-      if (threadIdx.x == 0) s_n = n_keys;
-      __syncthreads();
+      cut();
       continue;
     }
-    for (int i = threadIdx.x; i < take * pool_cap; i += blockDim.x) {
-      const int pi = c + i / pool_cap, j = i % pool_cap;
+    // one warp per pool, only the slots in use
+    for (int pi = c + warp; pi < c + take; pi += kFinalThreads / 32) {
       const size_t u = static_cast<size_t>(s_lists[pi / kEpiHalves]) * q_tiles + qt;
       const size_t slot = (u * kEpiHalves + (pi % kEpiHalves)) * kBM + ql;
-      if (j < static_cast<int>(counts[slot])) {
-        // the 32 pools of an epilogue warp are interleaved (pool_slot)
-        const uint64_t key = pools[(slot & ~size_t(31)) * pool_cap + pool_slot(ql & 31, j)];
+      const int cnt = static_cast<int>(counts[slot]);
+      // the 32 pools of an epilogue warp are interleaved (pool_slot)
+      const uint64_t* wpool = pools + (slot & ~size_t(31)) * pool_cap;
+      for (int j = lane; j < cnt; j += 32) {
+        const uint64_t key = wpool[pool_slot(ql & 31, j)];
         if (key != 0ull && static_cast<uint32_t>(key >> 32) >= lb) keys[atomicAdd(&s_n, 1)] = key;
       }
     }
@@ -898,7 +999,8 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
     __syncthreads();  // nobody appends again (next round) before everyone has read the count
     c += take;
   }
-  block_sort_prefix(keys, n_keys);
+  cut();
+  block_sort_prefix(keys, n_keys);  // at most k_sel + 64 keys
   const int kept = min(n_keys, k_sel);
   // keys[0..kept) sorted descending by tensor-core score
   if (carry_out != nullptr) {
@@ -975,28 +1077,11 @@ seed_threshold_kernel(const float* __restrict__ dump, int dump_ld, int n, int k_
     }
     __syncthreads();
     if (threadIdx.x < 32) {
-      // lane l owns bins 255 - 8l ... 248 - 8l (descending); find the bin holding the kk-th largest
-      unsigned mine = 0u;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) mine += hist[255 - 8 * lane - j];
-      unsigned incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
-      const unsigned hit = __ballot_sync(0xffffffffu, incl >= static_cast<unsigned>(kk));
-      const int owner = __ffs(hit) - 1;  // n >= k_sel guarantees a hit
-      if (lane == owner) {
-        unsigned cum = incl - mine;
-        int bin = 255 - 8 * lane;
-        for (int j = 0; j < 8; ++j, --bin) {
-          const unsigned h = hist[bin];
-          if (cum + h >= static_cast<unsigned>(kk)) break;
-          cum += h;
-        }
+      int bin, rank;
+      warp_find_bin_desc(hist, kk, lane, bin, rank);
+      if (lane == 0) {
         s_prefix = prefix | (static_cast<uint32_t>(bin) << shift);
-        s_k = kk - static_cast<int>(cum);
+        s_k = rank;
       }
     }
     __syncthreads();
