@@ -34,6 +34,13 @@
 // against the fp32 matrix (tensor-core inputs are rounded to tf32 / bf16; the north star asks for
 // 1e-5 fp32 scores) and writes the top k.
 //
+// Passes of one search (search_batch): (1) seed -- the first <= 32 tiles are multiplied as a plain
+// GEMM with the scores written out, a radix select gives each query's k_sel-th best as a starting
+// threshold; (2) sample (large stores) -- 1/16 of the tiles is searched and merged, its exact k_sel-th
+// best per query seeds (3) the main pass over the remaining tiles; both merges carry their lists
+// into the final top k.  Every bound used to drop a candidate is a proven lower bound of the
+// query's final k_sel-th best, so the result is exact regardless of timing.
+//
 // Tensor-core roofline: algorithmic flops = 2 * Q * N * dim per batch.
 #include <cuda.h>
 
