@@ -427,3 +427,33 @@ class ShardedStore:
 
     def close(self) -> None:
         self.local.close()
+
+
+def _sharded_engine_factory(dim: int, **kw):
+    return ShardedStore(dim, **kw)
+
+
+def _make_sharded_db_class():
+    from .db import PicoVectorDB
+
+    class ShardedPicoVectorDB(PicoVectorDB):
+        """``PicoVectorDB`` whose vectors are row-sharded over the ranks of the default process group.
+
+        SPMD: construct it and call it identically on every rank (one process per GPU under
+        ``torchrun``, ``device=LOCAL_RANK``); ``capacity=`` is required.  ids and documents are
+        replicated, vectors / scans / dict filters are per shard, ``save()`` writes ONE store in the
+        reference's file format (rank 0: ids + documents, every rank: its rows of the matrix).
+        """
+
+        _engine_factory = staticmethod(_sharded_engine_factory)
+
+    return ShardedPicoVectorDB
+
+
+def __getattr__(name: str):
+    # lazily built so importing this module never imports db.py (and the CUDA library) by itself
+    if name == "ShardedPicoVectorDB":
+        cls = _make_sharded_db_class()
+        globals()[name] = cls
+        return cls
+    raise AttributeError(name)

@@ -73,13 +73,10 @@ import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["PVDB_ROOT"])
 from oracle import picovdb_oracle as O
 from picovdb_b200 import K_ID, K_VECTOR, PicoVectorDB
-from picovdb_b200.sharded import ShardedStore, shard_range
+from picovdb_b200.sharded import ShardedPicoVectorDB as ShardedDB, shard_range
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-
-class ShardedDB(PicoVectorDB):
-    _engine_factory = staticmethod(lambda dim, **kw: ShardedStore(dim, **kw))
 
 path = os.path.join(os.environ["PVDB_TMP"], "db")
 n, dim = 5000, 64
