@@ -335,6 +335,7 @@ class PicoVectorDB:
         )
         self._host_cache: Optional[np.ndarray] = None  # lazily downloaded copy behind `_vectors`
         self._columns: dict[str, _ColumnIndex] = {}    # metadata key -> columnar index (lazy)
+        self._col_lock = threading.RLock()             # guards _columns and the device mirrors among readers
         self._load_or_init()
 
     # ------------------------------------------------------------------ host mirror of the matrix
@@ -696,16 +697,18 @@ class PicoVectorDB:
         if isinstance(where, dict) and len(where) == 1:
             ((key, val),) = where.items()
             is_in = isinstance(val, dict) and set(val.keys()) == {"$in"}
-            col = self._columns.get(key) if isinstance(key, str) else None
-            if col is None and isinstance(key, str):
-                col = self._columns[key] = _ColumnIndex(key, docs)
-            if col is not None and col.ok:
-                try:
-                    hit = col.match(set(val["$in"]) if is_in else (val,), n)
-                except TypeError:  # unhashable filter value
-                    hit = None
-                if hit is not None:
-                    return hit if ids is None else (hit & mask)
+            with self._col_lock:  # concurrent readers share (and lazily build) the column index
+                col = self._columns.get(key) if isinstance(key, str) else None
+                if col is None and isinstance(key, str):
+                    col = self._columns[key] = _ColumnIndex(key, docs)
+                hit = None
+                if col is not None and col.ok:
+                    try:
+                        hit = col.match(set(val["$in"]) if is_in else (val,), n)
+                    except TypeError:  # unhashable filter value
+                        hit = None
+            if hit is not None:
+                return hit if ids is None else (hit & mask)
             if isinstance(val, dict) and set(val.keys()) == {"$in"}:
                 wanted = set(val["$in"])
                 keep = [i for i in base_rows if docs[i] is not None and docs[i].get(key) in wanted]
@@ -799,15 +802,22 @@ class PicoVectorDB:
                 return [[] for _ in range(num_q)]  # also for a single query (reference quirk Q2)
             filtered = ids is not None or where is not None
             base = top_k + self._adaptive_buffer if filtered else top_k
-            dev = self._device_where(where, ids) if base >= 1 else None
+            dev = None
+            if isinstance(where, dict) and base >= 1:
+                # queries run under the READ lock, concurrently: the column index and its device mirror
+                # (slot numbers, rows sent so far) are shared state, so the bookkeeping and the search
+                # that relies on it are serialised among filtered queries
+                with self._col_lock:
+                    dev = self._device_where(where, ids)
+                    if dev is not None:
+                        # dict filter evaluated on the device from the code column: no host mask, no upload
+                        slot, wanted, extra = dev
+                        if not wanted:
+                            return [[] for _ in range(num_q)]
+                        scores, rows, n_cand = self._engine.search_where(
+                            raw, int(base), slot, wanted, extra, precision=self._precision
+                        )
             if dev is not None:
-                # dict filter evaluated on the device from the code column: no host mask, no upload
-                slot, wanted, extra = dev
-                if not wanted:
-                    return [[] for _ in range(num_q)]
-                scores, rows, n_cand = self._engine.search_where(
-                    raw, int(base), slot, wanted, extra, precision=self._precision
-                )
                 if n_cand == 0:
                     return [[] for _ in range(num_q)]
                 k_eff = min(base, n_cand)

@@ -174,3 +174,41 @@ def test_device_where_column_eviction(make_db):
             assert set(_ids_of(res)) == want
     slots = [c.dev_slot for c in db._columns.values() if c.dev_slot is not None]
     assert len(slots) == len(set(slots)) <= 16
+
+
+def test_concurrent_filtered_queries_share_the_column_index(make_db):
+    """Queries run under the read lock, concurrently; the lazily built column index and its device
+    mirror are shared state -- many threads filtering on many keys must all get the loop's answer."""
+    import threading
+
+    db = make_db(dim=8)
+    rng = np.random.default_rng(9)
+    keys = [f"k{j}" for j in range(20)]  # more keys than device column slots: eviction happens under load
+    n = 300
+    db.upsert([{K_VECTOR: rng.standard_normal(8), K_ID: f"r{i}", **{k: (i * (j + 1)) % 4 for j, k in enumerate(keys)}}
+               for i in range(n)])
+    q = rng.standard_normal(8).astype(np.float32)
+    errors = []
+
+    def worker(t):
+        try:
+            for rep_ in range(6):
+                for j, k in enumerate(keys):
+                    if (j + t) % 3:
+                        continue
+                    want = {f"r{i}" for i in range(n) if (i * (j + 1)) % 4 == 1}
+                    res = db.query(q, top_k=n, where={k: 1})
+                    if res and isinstance(res[0], list):   # no candidates: the reference's [[]]
+                        res = res[0]
+                    got = {r[K_ID] for r in res}
+                    if got != want:
+                        errors.append((t, k, len(got), len(want)))
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:5]
