@@ -217,6 +217,7 @@ class ShardedStore:
     matrix is the concatenation of the shards); upserts and deletes touch the owning shard only;
     a search is every rank's local scan + one all-gather + the merge kernel (``ShardedSearch``).
     The partition needs a fixed row capacity (``reserve_rows`` / PicoVectorDB's ``capacity=``).
+    Most methods contain a collective: call them in the same order on every rank, from one thread.
 
     ``local_factory`` / ``merge`` are test hooks (gloo process groups without GPUs).
     """
