@@ -482,3 +482,16 @@ def test_logging_quiet_by_default_and_timed_at_debug(make_db, caplog):
         db.save()
     msgs = [r.getMessage() for r in caplog.records]
     assert any(m.startswith("query took") for m in msgs) and any(m.startswith("save took") for m in msgs)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tests"), reason="reference tree not present")
+def test_reference_suite_passes_against_the_drop_in_class():
+    """The reference's own tests, run in place with `import picovdb` resolving to this package."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "run_reference_tests.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout
