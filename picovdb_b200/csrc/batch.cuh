@@ -12,6 +12,9 @@ constexpr int64_t kBatchMinQueries = 2;  // measured: one tensor-core pass (84 %
 
 bool batch_path_available();
 // largest k the fused tensor-core path selects in one pass (larger k uses the paged scan path)
+// Rows the prepared query matrix must hold for a batch of nq queries: whole 128-row TMA boxes
+// (zero rows past nq).
+int64_t batch_query_rows(int64_t nq);
 int batch_max_k(bool use_bf16, bool rescore);
 
 // d_qn: nq x ldq normalised fp32 queries; d_qn16: the same in bf16 (only for use_bf16).
