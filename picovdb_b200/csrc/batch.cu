@@ -1290,8 +1290,11 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
     CUtensorMap mq;
     // the caller pads the prepared queries with zero rows to whole TMA boxes (batch_query_rows)
     const int64_t nq_box = batch_query_rows(nq);
-    if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, s->dim, nq_box, s->ldq, kBM));
-    else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, s->dim, nq_box, s->ldq, kBM));
+    // K extent = whole boxes: the query rows are zero padded up to ldq, so the database map below may
+    // let the last box of a row run into the next row's first values (finite; times zero)
+    const int k_ext = p.k_blocks * (use_bf16 ? 64 : 32);
+    if (use_bf16) PVDB_TRY(encode_map(&mq, true, d_qn16 + q0 * s->ldq, k_ext, nq_box, s->ldq, kBM));
+    else PVDB_TRY(encode_map(&mq, false, d_qn + q0 * s->ldq, k_ext, nq_box, s->ldq, kBM));
 
     auto run_pass = [&](int tile_begin, int n_tiles, const float* thr_in, const uint64_t* carry_in, uint64_t* carry_out,
                         float* thr_out, bool pin_query_tiles, bool dump_scores = false) -> int {
@@ -1312,7 +1315,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       int max_units = 0;
       PVDB_TRY(batch_max_units(kern, cl, &max_units));
       CUtensorMap mdb;  // box = the rows one CTA fetches per K block
-      PVDB_TRY(encode_map(&mdb, use_bf16, db_ptr, s->dim, s->capacity, db_ld, kBN / cl));
+      PVDB_TRY(encode_map(&mdb, use_bf16, db_ptr, k_ext, s->capacity, db_ld, kBN / cl));
       const int64_t n_visits = static_cast<int64_t>(n_tiles) * ((p.q_tiles + cl - 1) / cl);
       const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, max_units));
       // pinned schedule: stride = (query-tile pairs) x (units per pair), so a unit never changes pair

@@ -330,9 +330,10 @@ int pvdb_store::ensure_capacity(int64_t need_rows, cudaStream_t s) {
   // more memory (no copy), without it the step is a reallocate-and-copy
   int64_t cap = std::max<int64_t>(need_rows, capacity + capacity / 2);
   cap = (cap + 1023) & ~int64_t(1023);
-  if (flags & PVDB_STORE_F32) PVDB_TRY(f32.grow(static_cast<size_t>(cap) * ld_f32 * sizeof(float), s));
+  // + kTailSlack: the batch path's last K box of a row may extend past the row (see encode_map)
+  if (flags & PVDB_STORE_F32) PVDB_TRY(f32.grow(static_cast<size_t>(cap) * ld_f32 * sizeof(float) + kTailSlack, s));
   if (flags & PVDB_STORE_BF16)
-    PVDB_TRY(bf16.grow(static_cast<size_t>(cap) * ld_bf16 * sizeof(__nv_bfloat16), s));
+    PVDB_TRY(bf16.grow(static_cast<size_t>(cap) * ld_bf16 * sizeof(__nv_bfloat16) + kTailSlack, s));
   PVDB_TRY(active.grow(static_cast<size_t>(cap / 32) * sizeof(uint32_t), s));
   for (DeviceBuffer& col : column)
     if (col.ptr) PVDB_TRY(col.grow(static_cast<size_t>(cap) * sizeof(uint32_t), s));
@@ -379,7 +380,7 @@ extern "C" int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_
   s->dim = dim;
   s->ld_f32 = (dim + 3) & ~3;
   s->ld_bf16 = (dim + 7) & ~7;
-  s->ldq = (dim + 7) & ~7;
+  s->ldq = (dim + 63) & ~63;  // whole K boxes of the batch path's TMA loads (32 fp32 / 64 bf16), zero padded
   s->flags = flags;
   s->h_pinned.pinned_host = true;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);

@@ -44,12 +44,15 @@ int build_column_filter(pvdb_store* s, int column, const int32_t* wanted, int n_
                         const uint32_t** d_bits_out, unsigned long long** d_count_out, cudaStream_t st);
 }  // namespace pvdb
 
+// bytes kept allocated past the last row of the fp32 / bf16 matrices
+constexpr size_t kTailSlack = 256;
+
 struct pvdb_store {
   int device = 0;
   int dim = 0;
   int ld_f32 = 0;   // fp32 row stride in elements (multiple of 4 -> 16-byte aligned rows)
   int ld_bf16 = 0;  // bf16 row stride in elements (multiple of 8 -> 16-byte aligned rows)
-  int ldq = 0;      // padded query length in floats (multiple of 8, zero padded)
+  int ldq = 0;      // padded query length in floats (multiple of 64, zero padded)
   int flags = 0;
   int64_t rows = 0;      // high-water mark of slots in use
   int64_t capacity = 0;  // slots allocated (multiple of 1024)
