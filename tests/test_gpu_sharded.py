@@ -99,6 +99,10 @@ db.save()
 db.close()
 db2 = ShardedDB(embedding_dim=dim, storage_file=path, capacity=8192, no_faiss=True, device=lr)
 res2 = db2.query(q, top_k=8)
+db2.vacuum()                                   # compaction moves rows between the shards
+res3 = db2.query(q, top_k=8)
+res3_w = db2.query(q, top_k=8, where={"cat": 2})   # columns were dropped by the compaction and are re-sent
+n_after = len(db2)
 db2.close()
 if rank == 0:
     store = O.normalize_rows(vecs)
@@ -108,6 +112,7 @@ if rank == 0:
     ids = lambda rs: [[r[K_ID] for r in lst] for lst in rs]
     want = [[f"r{j}" for j in row] for row in ref_r]
     assert ids(res) == want and ids(res2) == want and [r[K_ID] for r in one] == want[0]
+    assert ids(res3) == want and ids(res3_w) == ids(res_w) and n_after == int(alive.sum())
     ref_s2, ref_r2 = O.search(store, qn, 8 + 32, alive, (np.arange(n) % 5) == 2)
     assert ids(res_w) == [[f"r{j}" for j in row[:8]] for row in ref_r2]
     pf = np.isin(np.arange(n) % 5, [1, 4]) & (np.arange(n) % 3 == 0)
