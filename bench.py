@@ -4,45 +4,77 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload at every N: BASELINE.json configs[1] -- 1,000,000 x 1024 fp32 unit-norm rows (synthetic
-N(0,1) -> L2-normalised, DB seed 123 (+rank), query seed 99), single-query top-10 through the
-HBM-bound scan kernel.  One "step" = `--queries-per-step` (32) independent single queries, each
-answered by its own pass of the scan kernel over the whole (shard of the) matrix.  For N > 1 the
-rows are sharded contiguously over the ranks (strong scaling: the database is fixed), every rank
-scans its shard for each query of the step, and ONE all-gather + merge kernel per step combines
-the per-rank top-10 lists (picovdb_b200/sharded.py).
+Workload at every N (the north-star target config, BASELINE.json configs[4]; 76.8 GB, fits one
+B200): **C5 = 100,000,000 x 384 unit-norm rows kept as a bf16 mirror only**, synthetic N(0,1) ->
+L2-normalised, DB seed 123 (+rank), query seed 99.  Rows are sharded contiguously over the N ranks
+(strong scaling: the database is fixed).
 
-`value`  = queries/s with queries and results resident in HBM (CUDA events, max over ranks).
-`e2e`    = queries/s through the public host API (`DeviceStore.search`, i.e. the `pvdb_search`
-           C-ABI call): ONE query per call, query in pinned host memory, H2D + kernels + D2H +
-           stream sync inside the timed region (wall clock around the blocking calls).
-`roofline` = the scan kernel alone (pre-normalised query => the only kernel launched), CUDA
-           events around back-to-back launches; algorithmic bytes = rows*dim*4 + rows/8.
+The JSON line carries three measurements of that store:
+
+`value` / `roofline` / `e2e`  -- SINGLE queries, top-10, through the HBM-bound scan kernel.  One "step"
+    = `--queries-per-step` (32) independent single queries, each answered by its own pass of the scan
+    kernel over the whole (shard of the) mirror; for N > 1 every rank scans its shard and the per-rank
+    top-10 lists are exchanged and merged (picovdb_b200/sharded.py).
+    value    = queries/s, queries and results resident in HBM (CUDA events, max over ranks).
+    e2e      = queries/s through the public host API (`pvdb_search`: ONE query per call, query in host
+               memory, H2D + kernels + D2H + stream sync inside the timed region, wall clock).
+    roofline = the scan kernel alone (pre-normalised query => the only kernel launched), CUDA events
+               around back-to-back launches; algorithmic bytes = rows*dim*2 + rows/8 per launch.
+`batch`  -- the same store answering a 4096-query batch, top-10, through the tcgen05 tensor-core kernel
+    (+ exact re-scoring, exactness guard): queries/s device-resident and end to end with host buffers,
+    `roofline.bound = "tensor"` with algorithmic flops 2*Q*N*dim against the measured bf16 peak (burst
+    and sustained), recall@10 against the exact scan of the same store AND against an independent
+    fp32 brute force (torch matmul over the pre-rounding rows) on 64 sampled queries.
+`c2`     -- (N = 1 only) BASELINE configs[1]: 1,000,000 x 1024 fp32, single-query top-10, with the
+    oracle port timed on the SAME full-size matrix on the host (`c2.cpu_baseline`).
+
+`parity` -- checked inside this run, before timing: single-query and batch results of 64 sampled
+    queries against the fp32 brute force (bf16 tolerance 1e-2; ids must agree wherever the reference
+    score gap exceeds it) and, for N > 1, the device-side exchange + merge against a host merge of
+    every rank's local list (bit-equal) with every row inside its owner's shard.
 `cpu_baseline` / `--impl reference` = the oracle's numpy restatement of the reference path
-           (oracle/picovdb_oracle.py: sgemv + argpartition + argsort, all host threads) on the same
-           1M x 1024 workload, a bounded number of single queries.
+    (oracle/picovdb_oracle.py: sgemv + argpartition + argsort, all host threads).  The reference
+    keeps fp32 rows only: 100M x 384 fp32 = 154 GB does not fit the host, so the CPU arm times single
+    queries over a BOUNDED fp32 sample of the same rows and scales the time linearly in the row count
+    (an explicitly labelled extrapolation; the scan is linear in rows).
 
-The input (4.1 GB per query pass) is far larger than the 126 MB L2, so no L2 flush is needed
+Inputs per pass (>= 9.6 GB per GPU) are far larger than the 126 MB L2, so no L2 flush is needed
 between iterations (stated in `config.l2`).
 """
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import statistics
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+
+def usable_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv:
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU
+    # measurement that must use all the host threads it can at every N -- set before OpenBLAS loads
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(usable_cores())
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "queries/sec (top-10, exact)"
 UNIT = "queries/s"
+N_REF = 64  # sampled queries checked against the independent fp32 brute force
 
 
 def parse_args():
@@ -51,39 +83,56 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
-                    help="c2 (default, BASELINE configs[1]): 1M x 1024 fp32; c5: 100M x 384 bf16 mirror only "
-                         "(the north-star target config, single queries), sharded over the ranks")
+    ap.add_argument("--workload", default="c5", choices=["c2", "c5"],
+                    help="c5 (default, the north-star target): 100M x 384 bf16 mirror only; "
+                         "c2 (BASELINE configs[1]): 1M x 1024 fp32")
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries-per-step", type=int, default=32)
-    ap.add_argument("--cpu-queries", type=int, default=24, help="single queries timed for cpu_baseline")
+    ap.add_argument("--batch-queries", type=int, default=4096)
+    ap.add_argument("--batch-iters", type=int, default=5)
+    ap.add_argument("--no-batch", action="store_true")
+    ap.add_argument("--no-c2", action="store_true")
+    ap.add_argument("--cpu-queries", type=int, default=16, help="single queries timed for cpu_baseline")
+    ap.add_argument("--cpu-sample-rows", type=int, default=8_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)  # timing hygiene: never fewer than 3 untimed warm-up steps
-    if args.workload == "c5":
-        args.rows = args.rows or 100_000_000
-        args.dim = args.dim or 384
-        args.store_dtype, args.precision, args.elem_bytes = "bf16", "bf16", 2
-    else:
-        args.rows = args.rows or 1_000_000
-        args.dim = args.dim or 1024
-        args.store_dtype, args.precision, args.elem_bytes = "f32", "f32", 4
+    apply_workload(args, args.workload)
     return args
 
 
-def workload_config(args, world):
+def apply_workload(args, name: str):
+    args.workload = name
+    if name == "c5":
+        args.rows = args.rows or 100_000_000
+        args.dim = args.dim or 384
+        args.store_dtype, args.precision, args.elem_bytes, args.tol = "bf16", "bf16", 2, 1e-2
+    else:
+        args.rows = args.rows or 1_000_000
+        args.dim = args.dim or 1024
+        args.store_dtype, args.precision, args.elem_bytes, args.tol = "f32", "f32", 4, 1e-5
+    return args
+
+
+def workload_config(args):
+    world = args.gpus
+    what = "bf16 mirror only" if args.store_dtype == "bf16" else "fp32"
     return {
-        "workload": (f"{args.workload.upper()}: {args.rows}x{args.dim} {args.store_dtype} unit-norm rows, "
-                     f"single-query top-{args.k} (HBM-bound scan)"),
+        "workload": (f"{args.workload.upper()}: {args.rows}x{args.dim} unit-norm rows ({what}), "
+                     f"single-query top-{args.k} (HBM-bound scan) + {args.batch_queries}-query batch "
+                     f"(tcgen05 path) on the same store"),
         "rows": args.rows,
         "dim": args.dim,
         "k": args.k,
         "queries_per_step": args.queries_per_step,
+        "batch_queries": args.batch_queries,
         "sharding": f"rows/{world} contiguous per rank" if world > 1 else "none",
-        "exchange": "one all-gather + merge kernel per step" if world > 1 else "none",
-        "l2": f"inputs ({args.rows * args.dim * args.elem_bytes / world / 1e9:.1f} GB per pass per GPU) larger than L2 (126 MB): no flush needed",
+        "exchange": "per-rank top-k lists exchanged + merged on the device, once per query (batch: once per batch)"
+                    if world > 1 else "none",
+        "l2": (f"inputs ({args.rows * args.dim * args.elem_bytes / world / 1e9:.1f} GB per pass per GPU) "
+               "larger than L2 (126 MB): no flush needed"),
         "seeds": {"db": 123, "queries": 99},
     }
 
@@ -155,40 +204,43 @@ def host_matrix(rows: int, dim: int, seed: int) -> np.ndarray:
         g = np.random.default_rng([seed, i0])
         out[i0:i1] = O.normalize_rows_fast(g.standard_normal((i1 - i0, dim), dtype=np.float32))
 
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(32, usable_cores())) as ex:
         list(ex.map(fill, range(0, rows, chunk)))
     return out
 
 
-def blas_threads() -> int:
+def set_blas_threads() -> int:
+    """Pin the BLAS pool to every usable core (it would otherwise follow OMP_NUM_THREADS, which
+    torch.distributed.run sets to 1) and return the thread count actually in effect."""
+    want = usable_cores()
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_info, threadpool_limits
 
-        return max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
+        threadpool_limits(limits=want, user_api="blas")
+        got = [p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(got or [want])
     except Exception:
-        return os.cpu_count() or 1
+        return want
 
 
-def cpu_rows_that_fit(args) -> int:
+def cpu_sample_rows(args) -> int:
+    """Rows of the fp32 sample the CPU arm scans: the whole matrix when it fits comfortably in host
+    RAM, else a bounded sample (time is then scaled linearly to the full row count)."""
     try:
         import psutil
 
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 16 << 30
-    need = args.rows * args.dim * 4
-    if args.workload == "c5":
-        return min(args.rows, 2_000_000)  # the reference holds fp32 only: 100M x 384 = 154 GB; bounded sample
-    if need * 1.3 < avail:
-        return args.rows
-    return max(1, int(avail / 1.3 / (args.dim * 4)))
+    fit = int(avail / 2.5 / (args.dim * 4))
+    return max(1, min(args.rows, args.cpu_sample_rows, fit))
 
 
 def time_oracle(args, n_queries: int, warm: int = 2):
     """Seconds per single query of the oracle port on this host (median), plus a description."""
     from oracle import picovdb_oracle as O
 
-    rows = cpu_rows_that_fit(args)
+    rows = cpu_sample_rows(args)
     mat = host_matrix(rows, args.dim, 123)
     qs = np.random.default_rng(99).standard_normal((n_queries + warm, args.dim)).astype(np.float32)
     times = []
@@ -200,11 +252,12 @@ def time_oracle(args, n_queries: int, warm: int = 2):
         if i >= warm:
             times.append(dt)
     per_query = statistics.median(times)
-    scale = rows / args.rows  # < 1 only when the full matrix does not fit in host RAM
     sample = f"{n_queries} single queries over {rows}x{args.dim} fp32 on the host"
     if rows != args.rows:
-        sample += f" (bounded sample; time scaled linearly to {args.rows} rows)"
-        per_query = per_query / scale
+        sample += (f" (bounded sample of the {args.rows}-row workload: the reference keeps fp32 rows only; "
+                   f"per-query time scaled linearly x{args.rows / rows:.1f} to {args.rows} rows -- extrapolation)")
+        per_query = per_query * (args.rows / rows)
+    del mat
     return per_query, sample, times
 
 
@@ -213,8 +266,8 @@ def run_reference_arm(args, world, rank):
     (a Python reference cannot travel to the GPU box)."""
     if rank != 0:
         return
-    threads = blas_threads()
-    per_step_q = max(1, min(args.queries_per_step, 4))
+    threads = set_blas_threads()
+    per_step_q = max(1, min(args.queries_per_step, 2))
     n = per_step_q * args.steps
     t0 = time.perf_counter()
     per_query, sample, times = time_oracle(args, n, warm=max(1, min(args.warmup, 3)))
@@ -233,23 +286,27 @@ def run_reference_arm(args, world, rank):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{sample}; {per_step_q} queries per step"},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "host": {"cpu_count": os.cpu_count(), "blas_threads": threads, "wall_s": time.perf_counter() - t0},
+        "host": {"cpu_count": os.cpu_count(), "usable_cores": usable_cores(), "blas_threads": threads,
+                 "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"), "wall_s": time.perf_counter() - t0},
     }
     emit_json(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def load_peaks():
+def load_peaks() -> dict:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            j = json.load(f)
+        return {"hbm": float(j["hbm_gbs"]), "bf16": float(j["bf16_tflops"]),
+                "bf16_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "bf16": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 def load_traffic(key: str):
@@ -258,6 +315,66 @@ def load_traffic(key: str):
         with open(path) as f:
             return json.load(f).get(key)
     return None
+
+
+def fill_store(torch, store, dev, n_local, dim, seed, ref_qn, k):
+    """Generate this rank's rows on the device (N(0,1), normalised + stored by the fused upsert
+    kernel) and, on the way, keep an independent fp32 brute-force top-k of the `ref_qn` queries over
+    the SAME rows before any rounding: torch normalise + fp32 matmul + topk, chunk by chunk."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    chunk = 131072
+    stream = torch.cuda.current_stream().cuda_stream
+    best_s = torch.full((ref_qn.shape[0], k), float("-inf"), device=dev)
+    best_r = torch.full((ref_qn.shape[0], k), -1, dtype=torch.int64, device=dev)
+    for c0 in range(0, n_local, chunk):
+        m = min(chunk, n_local - c0)
+        x = torch.randn(m, dim, device=dev, generator=gen)
+        store.upsert_range_dev(x.data_ptr(), c0, m, stream=stream)  # fused normalise + scatter
+        xn = torch.nn.functional.normalize(x, dim=1)
+        sc = ref_qn @ xn.T                                           # fp32 (TF32 matmul is off by default)
+        s, r = torch.topk(sc, min(k, m), dim=1)
+        cs = torch.cat([best_s, s], dim=1)
+        cr = torch.cat([best_r, r + c0], dim=1)
+        best_s, idx = torch.topk(cs, k, dim=1)
+        best_r = torch.gather(cr, 1, idx)
+        torch.cuda.synchronize()
+    return best_s, best_r
+
+
+def host_merge(scores_list, rows_list, k):
+    """numpy k-way merge of per-rank (Q, k) lists: (score desc, row asc), -1 rows last."""
+    s = np.concatenate(scores_list, axis=1)
+    r = np.concatenate(rows_list, axis=1)
+    out_s = np.full((s.shape[0], k), -np.inf, dtype=np.float32)
+    out_r = np.full((s.shape[0], k), -1, dtype=np.int64)
+    for q in range(s.shape[0]):
+        ok = r[q] >= 0
+        order = np.lexsort((r[q][ok], -s[q][ok].astype(np.float64)))[:k]
+        out_s[q, : order.size] = s[q][ok][order]
+        out_r[q, : order.size] = r[q][ok][order]
+    return out_s, out_r
+
+
+def check_against_reference(got_s, got_r, ref_s, ref_r, tol):
+    """The north star's id rule: scores of common rows agree within `tol` (relative, + small
+    absolute), and a reference row may be missing from the result only if its reference score is
+    within the tolerance band of the reference k-th score.  Returns (recall, violations)."""
+    hits = total = bad = 0
+    for q in range(ref_r.shape[0]):
+        kth = ref_s[q, -1]
+        band = 2.0 * tol * max(abs(float(kth)), 1e-3)
+        got = {int(r): float(s) for r, s in zip(got_r[q], got_s[q])}
+        for r, s in zip(ref_r[q], ref_s[q]):
+            total += 1
+            g = got.get(int(r))
+            if g is None:
+                if s > kth + band:
+                    bad += 1
+                continue
+            hits += 1
+            if abs(g - float(s)) > tol * abs(float(s)) + 1e-5:
+                bad += 1
+    return hits / max(total, 1), bad
 
 
 def run_b200(args, world, rank, local_rank):
@@ -277,171 +394,334 @@ def run_b200(args, world, rank, local_rank):
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-
-    r0, r1 = shard_range(args.rows, world, rank)
-    n_local = r1 - r0
-    store = DeviceStore(args.dim, device=local_rank, reserve_rows=max(n_local, 1),
-                        keep_f32=args.store_dtype == "f32", bf16_mirror=args.store_dtype == "bf16")
-    gen = torch.Generator(device=dev).manual_seed(123 + rank)
-    chunk = 131072
+    peaks = load_peaks()
     stream = torch.cuda.current_stream().cuda_stream
-    for c0 in range(0, n_local, chunk):
-        m = min(chunk, n_local - c0)
-        x = torch.randn(m, args.dim, device=dev, generator=gen)
-        store.upsert_range_dev(x.data_ptr(), c0, m, stream=stream)  # fused normalise + scatter
-        torch.cuda.synchronize()
-    sharded = ShardedSearch(store, r0)
-
-    qps, k = args.queries_per_step, args.k
-    total_steps = args.steps + args.warmup
-    qgen = torch.Generator(device="cpu").manual_seed(99)
-    n_pool = qps * min(total_steps, 8)
-    q_host = torch.randn(n_pool, args.dim, generator=qgen).pin_memory()
-    q_dev = q_host.to(dev)
-    q_np = q_host.numpy()
-
-    def step_device(i):
-        sl = q_dev[(i % (n_pool // qps)) * qps:][:qps]
-        return sharded.search_dev(sl, k, precision=args.precision, scan_only=True)  # one scan pass per query
-
-    # ---- sanity: results sorted, rows valid, all ranks agree (full parity lives in tests/)
-    s0, r0_ = step_device(0)
-    torch.cuda.synchronize()
-    s_chk, r_chk = s0.cpu().numpy(), r0_.cpu().numpy()
-    assert np.all(np.diff(s_chk, axis=1) <= 0) and r_chk.min() >= 0 and r_chk.max() < args.rows
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident inputs/outputs (clock sampling starts before the warm-up so that
-    # short timed regions still get samples taken under load)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
-    # nvidia-smi needs ~1 s before its first sample: when the whole timed region is shorter than that
-    # (sharded runs: a few ms per step), keep the GPUs under the same load with extra untimed steps --
-    # the same number on every rank, the steps contain a collective
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    for i in range(3):
-        step_device(i)
-    pe1.record()
-    torch.cuda.synchronize()
-    probe = torch.tensor([pe0.elapsed_time(pe1) / 3.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(probe, op=dist.ReduceOp.MAX)
-    step_ms = max(float(probe.item()), 1e-3)
-    if step_ms * args.steps < 1500.0:
-        for i in range(min(20000, int((1500.0 - step_ms * args.steps) / step_ms) + 1)):
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t.cpu()]
+
+    def measure(wl, sampler=None, with_batch=True):
+        """Build the store of workload `wl` on this rank's shard, check it, time it."""
+        r0, r1 = shard_range(wl.rows, world, rank)
+        n_local = r1 - r0
+        k, qps = wl.k, wl.queries_per_step
+        total_steps = wl.steps + wl.warmup
+        qgen = torch.Generator(device="cpu").manual_seed(99)
+        n_pool = max(qps * min(total_steps, 8), N_REF)
+        nb = wl.batch_queries if with_batch else 0
+        q_host = torch.randn(max(n_pool, nb), wl.dim, generator=qgen).pin_memory()
+        q_dev = q_host.to(dev)
+        q_np = q_host.numpy()
+        ref_qn = torch.nn.functional.normalize(q_dev[:N_REF], dim=1).contiguous()
+
+        store = DeviceStore(wl.dim, device=local_rank, reserve_rows=max(n_local, 1),
+                            keep_f32=wl.store_dtype == "f32", bf16_mirror=wl.store_dtype == "bf16")
+        t_fill = time.perf_counter()
+        loc_s, loc_r = fill_store(torch, store, dev, n_local, wl.dim, 123 + rank, ref_qn, k)
+        loc_r = torch.where(loc_r >= 0, loc_r + r0, loc_r)
+        fill_s = time.perf_counter() - t_fill
+        sharded = ShardedSearch(store, r0)
+
+        def gather_lists(s, r):
+            """every rank's (Q, k) lists on the host, in rank order"""
+            if world == 1:
+                return [s.cpu().numpy()], [r.cpu().numpy()]
+            ss = [torch.empty_like(s) for _ in range(world)]
+            rr = [torch.empty_like(r) for _ in range(world)]
+            dist.all_gather(ss, s.contiguous())
+            dist.all_gather(rr, r.contiguous())
+            return [x.cpu().numpy() for x in ss], [x.cpu().numpy() for x in rr]
+
+        # ---- parity, before any timing ---------------------------------------------------------
+        parity = {}
+        ref_s, ref_r = host_merge(*gather_lists(loc_s, loc_r), k)        # fp32 brute force, all shards
+        # (a) single queries through the sharded device path
+        s_one = torch.empty((N_REF, k), dtype=torch.float32, device=dev)
+        r_one = torch.empty((N_REF, k), dtype=torch.int64, device=dev)
+        for i in range(N_REF):
+            s, r = sharded.search_dev(q_dev[i:i + 1], k, precision=wl.precision, scan_only=True)
+            s_one[i], r_one[i] = s[0], r[0]
+        torch.cuda.synchronize()
+        one_s, one_r = s_one.cpu().numpy(), r_one.cpu().numpy()
+        assert np.all(np.diff(one_s, axis=1) <= 0) and one_r.min() >= 0 and one_r.max() < wl.rows
+        rec, bad = check_against_reference(one_s, one_r, ref_s, ref_r, wl.tol)
+        parity["single_recall_vs_fp32"] = rec
+        parity["single_violations"] = bad
+        # (b) N > 1: the device exchange + merge against a host merge of every rank's local list
+        if world > 1:
+            l_s = torch.empty((N_REF, k), dtype=torch.float32, device=dev)
+            l_r = torch.empty((N_REF, k), dtype=torch.int64, device=dev)
+            store.search_dev(q_dev.data_ptr(), N_REF, k, l_s.data_ptr(), l_r.data_ptr(), precision=wl.precision,
+                             stream=stream, scan_only=True)
+            torch.cuda.synchronize()
+            ls, lr = gather_lists(l_s, l_r)
+            in_shard = True
+            for j in range(world):
+                a, b = shard_range(wl.rows, world, j)
+                live = lr[j] >= 0
+                in_shard = in_shard and bool(np.all((lr[j][live] >= a) & (lr[j][live] < b)))
+            m_s, m_r = host_merge(ls, lr, k)
+            parity["merge_equals_host_merge"] = bool(np.array_equal(m_r, one_r) and np.array_equal(m_s, one_s))
+            parity["rows_in_owner_shard"] = in_shard
+        # (c) the batch path on the same queries
+        batch_out = None
+        if with_batch:
+            qb = q_dev[:nb]
+            sb, rb = sharded.search_dev(qb, k, precision=wl.precision)
+            torch.cuda.synchronize()
+            bs, br = sb[:N_REF].cpu().numpy(), rb[:N_REF].cpu().numpy()
+            rec_b, bad_b = check_against_reference(bs, br, ref_s, ref_r, wl.tol)
+            same = float(np.mean([len(set(br[q]) & set(one_r[q])) / k for q in range(N_REF)]))
+            parity["batch_recall_vs_fp32"] = rec_b
+            parity["batch_violations"] = bad_b
+            parity["batch_recall_vs_exact_scan"] = same
+            batch_out = {"recall_at_10_vs_exact_scan": same, "recall_at_10_vs_fp32": rec_b,
+                         "recall_queries": N_REF}
+        flags = torch.tensor([parity.get("single_violations", 0) + parity.get("batch_violations", 0),
+                              0 if parity.get("merge_equals_host_merge", True) else 1,
+                              0 if parity.get("rows_in_owner_shard", True) else 1], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        parity["checked"] = True
+        parity["ok"] = bool(flags.sum().item() == 0)
+        assert parity["ok"], f"parity check failed: {parity}"
+
+        # ---- value: device-resident single queries --------------------------------------------
+        def step_device(i):
+            sl = q_dev[(i % (n_pool // qps)) * qps:][:qps]
+            return sharded.search_dev(sl, k, precision=wl.precision, scan_only=True)  # one scan pass per query
+
+        if sampler is not None:
+            sampler.start()
+        for i in range(wl.warmup):
             step_device(i)
-    barrier()
-    launches0 = N.kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-    ev1.record()
-    barrier()
-    launches = N.kernel_launches() - launches0
-    dev_ms = ev0.elapsed_time(ev1)
+        barrier()
+        # nvidia-smi needs ~1 s before its first sample: when the whole timed region is shorter than that,
+        # keep the GPUs under the same load with extra untimed steps (same count on every rank)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for i in range(3):
+            step_device(i)
+        pe1.record()
+        torch.cuda.synchronize()
+        step_ms = max(max_over_ranks([pe0.elapsed_time(pe1) / 3.0])[0], 1e-3)
+        if step_ms * wl.steps < 1500.0:
+            for i in range(min(20000, int((1500.0 - step_ms * wl.steps) / step_ms) + 1)):
+                step_device(i)
+        barrier()
+        launches0 = N.kernel_launches()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(wl.steps):
+            step_device(wl.warmup + i)
+        ev1.record()
+        barrier()
+        launches = N.kernel_launches() - launches0
+        dev_ms = ev0.elapsed_time(ev1)
 
-    # ---- e2e: public host API, ONE query per call, pinned host query, result back on the host
-    def step_e2e(i):
-        base = (i % (n_pool // qps)) * qps
-        out = None
-        for j in range(qps):
-            out = sharded.search(q_np[base + j: base + j + 1], k, precision=args.precision) if world > 1 else \
-                store.search(q_np[base + j: base + j + 1], k, precision=args.precision)
-        return out
+        # ---- e2e: public host API, ONE query per call, host query in, host result out ---------
+        def one_e2e(qv):
+            return sharded.search(qv, k, precision=wl.precision) if world > 1 else \
+                store.search(qv, k, precision=wl.precision)
 
-    for i in range(min(args.warmup, 3)):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(args.warmup + i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+        def step_e2e(i):
+            base = (i % (n_pool // qps)) * qps
+            out = None
+            for j in range(qps):
+                out = one_e2e(q_np[base + j: base + j + 1])
+            return out
 
-    # ---- roofline of the dominant kernel: scan launches only (pre-normalised query)
-    n_qn = min(64, n_pool)
-    qn_dev = torch.nn.functional.normalize(q_dev[:n_qn], dim=1).contiguous()
-    out_s = torch.empty(k, dtype=torch.float32, device=dev)
-    out_r = torch.empty(k, dtype=torch.int64, device=dev)
-    n_scan = 50
-    for j in range(5):
-        store.search_dev(qn_dev[j].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision=args.precision,
-                         normalized=True, stream=stream)
-    torch.cuda.synchronize()
-    l0 = N.kernel_launches()
-    ev0.record()
-    for j in range(n_scan):
-        store.search_dev(qn_dev[j % n_qn].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(),
-                         precision=args.precision, normalized=True, stream=stream)
-    ev1.record()
-    torch.cuda.synchronize()
-    assert N.kernel_launches() - l0 == n_scan, "roofline loop must launch exactly one kernel per query"
-    scan_ms = ev0.elapsed_time(ev1) / n_scan
+        for i in range(min(wl.warmup, 3)):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(wl.steps):
+            step_e2e(wl.warmup + i)
+        barrier()
+        e2e_s = time.perf_counter() - t0
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, scan_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, scan_ms = [float(x) for x in times.cpu()]
+        # ---- batch: tensor-core path, device resident and end to end ---------------------------
+        b_ms = b_e2e_ms = None
+        if with_batch:
+            qb = q_dev[:nb]
+            for _ in range(3):
+                sharded.search_dev(qb, k, precision=wl.precision)
+            barrier()
+            bt = []
+            for _ in range(wl.batch_iters):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sharded.search_dev(qb, k, precision=wl.precision)
+                e1.record()
+                torch.cuda.synchronize()
+                bt.append(e0.elapsed_time(e1))
+            b_ms = statistics.median(bt)
+            qb_np = q_np[:nb]
+            one_e2e(qb_np)
+            barrier()
+            et = []
+            for _ in range(max(2, wl.batch_iters // 2)):
+                t0 = time.perf_counter()
+                one_e2e(qb_np)
+                et.append((time.perf_counter() - t0) * 1e3)
+            b_e2e_ms = statistics.median(et)
+        clocks = sampler.stop() if sampler is not None else None
+
+        # ---- roofline of the dominant single-query kernel: scan launches only ------------------
+        n_qn = min(64, n_pool)
+        qn_dev = torch.nn.functional.normalize(q_dev[:n_qn], dim=1).contiguous()
+        out_s = torch.empty(k, dtype=torch.float32, device=dev)
+        out_r = torch.empty(k, dtype=torch.int64, device=dev)
+        n_scan = 50
+        for j in range(5):
+            store.search_dev(qn_dev[j].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision=wl.precision,
+                             normalized=True, stream=stream)
+        torch.cuda.synchronize()
+        l0 = N.kernel_launches()
+        ev0.record()
+        for j in range(n_scan):
+            store.search_dev(qn_dev[j % n_qn].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(),
+                             precision=wl.precision, normalized=True, stream=stream)
+        ev1.record()
+        torch.cuda.synchronize()
+        assert N.kernel_launches() - l0 == n_scan, "roofline loop must launch exactly one kernel per query"
+        scan_ms = ev0.elapsed_time(ev1) / n_scan
+
+        dev_ms, e2e_ms, scan_ms, b_ms, b_e2e_ms, fill_s = max_over_ranks(
+            [dev_ms, e2e_s * 1e3, scan_ms, b_ms or 0.0, b_e2e_ms or 0.0, fill_s])
+        store.close()
+        del sharded, store
+        torch.cuda.empty_cache()
+
+        n_queries = wl.steps * qps
+        algo_bytes = n_local * wl.dim * wl.elem_bytes + n_local / 8
+        achieved = algo_bytes / (scan_ms / 1e3) / 1e9
+        res = {
+            "value": n_queries / (dev_ms / 1e3),
+            "ms_per_step": dev_ms / wl.steps,
+            "e2e": {
+                "value": n_queries / (e2e_ms / 1e3),
+                "unit": UNIT,
+                "h2d_bytes_per_step": qps * wl.dim * 4,
+                "d2h_bytes_per_step": qps * k * 12,
+                "api": ("DeviceStore.search -> pvdb_search" if world == 1 else "ShardedSearch.search")
+                       + " (one query per call; host query in, host result out; blocking)",
+            },
+            "gpu_launches": int(launches),
+            "roofline": {
+                "bound": "hbm",
+                "kernel": f"scan_topk_kernel<{wl.store_dtype}> (masked GEMV + fused top-k)",
+                "achieved": achieved,
+                "peak": peaks["hbm"],
+                "unit": "GB/s",
+                "frac": achieved / peaks["hbm"],
+                "peak_source": peaks["source"] + " hbm_gbs",
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "us_per_launch": scan_ms * 1e3,
+                "rows_per_gpu": n_local,
+                "traffic": load_traffic(f"scan_{wl.store_dtype}_{n_local}x{wl.dim}"),
+            },
+            "clocks": clocks,
+            "parity": parity,
+            "fill_seconds": fill_s,
+        }
+        if with_batch:
+            flops = 2.0 * nb * wl.rows * wl.dim
+            tf = flops / (b_ms / 1e3) / 1e12
+            kind = "bf16" if wl.store_dtype == "bf16" else "tf32 (peak taken as bf16 / 2)"
+            scale = 1.0 if wl.store_dtype == "bf16" else 0.5
+            batch_out.update({
+                "queries": nb,
+                "k": k,
+                "ms_per_batch": b_ms,
+                "value": nb / (b_ms / 1e3),
+                "unit": UNIT,
+                "roofline": {
+                    "bound": "tensor",
+                    "kernel": f"batch_topk_kernel<{kind}> (tcgen05.mma + fused mask/top-k epilogue) + finalize (re-score)",
+                    "flops": flops,
+                    "achieved": tf,
+                    "unit": "TFLOP/s",
+                    "peak": peaks["bf16"] * scale * world,
+                    "frac": tf / (peaks["bf16"] * scale * world),
+                    "peak_sustained": peaks["bf16_sustained"] * scale * world,
+                    "frac_sustained": tf / (peaks["bf16_sustained"] * scale * world),
+                    "peak_source": peaks["source"] + f" bf16_tflops / bf16_tflops_sustained x {world} GPU(s)",
+                },
+                "e2e": {
+                    "value": nb / (b_e2e_ms / 1e3),
+                    "unit": UNIT,
+                    "ms_per_batch": b_e2e_ms,
+                    "h2d_bytes_per_batch": nb * wl.dim * 4,
+                    "d2h_bytes_per_batch": nb * k * 12,
+                    "api": ("DeviceStore.search -> pvdb_search" if world == 1 else "ShardedSearch.search")
+                           + " (host query batch in, host results out; blocking)",
+                },
+            })
+            res["batch"] = batch_out
+        return res
+
+    # ---- the main workload -------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    main = measure(args, sampler=sampler, with_batch=not args.no_batch)
+
+    # ---- secondary block: BASELINE configs[1] at full size next to the CPU port (N = 1 only) ----
+    c2 = None
+    if world == 1 and args.workload == "c5" and not args.no_c2:
+        wl2 = argparse.Namespace(**vars(args))
+        wl2.rows = wl2.dim = None
+        apply_workload(wl2, "c2")
+        wl2.steps, wl2.warmup = max(5, min(args.steps, 10)), 3
+        r2 = measure(wl2, sampler=None, with_batch=False)
+        c2 = {"workload": f"C2: {wl2.rows}x{wl2.dim} fp32 unit-norm rows, single-query top-{wl2.k}",
+              "value": r2["value"], "unit": UNIT, "e2e": r2["e2e"], "roofline": r2["roofline"], "parity": r2["parity"]}
+        if not args.no_cpu_baseline:
+            threads = set_blas_threads()
+            per_query, sample, _ = time_oracle(wl2, args.cpu_queries)
+            c2["cpu_baseline"] = {"value": 1.0 / per_query, "unit": UNIT, "cores": threads, "kind": "port",
+                                  "sample": sample}
 
     if rank == 0:
-        n_queries = args.steps * qps
-        value = n_queries / (dev_ms / 1e3)
-        e2e_value = n_queries / (e2e_ms / 1e3)
-        peak, peak_src = load_peaks()
-        algo_bytes = n_local * args.dim * args.elem_bytes + n_local / 8
-        achieved = algo_bytes / (scan_ms / 1e3) / 1e9
         line = {
             "metric": METRIC,
-            "value": value,
+            "value": main["value"],
             "unit": UNIT,
             "n_gpus": world,
             "steps": args.steps,
             "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps,
+            "ms_per_step": main["ms_per_step"],
             "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None,
             "dtype": args.store_dtype,
             "data": "synthetic",
-            "config": workload_config(args, world),
-            "e2e": {
-                "value": e2e_value,
-                "unit": UNIT,
-                "h2d_bytes_per_step": qps * args.dim * 4,
-                "d2h_bytes_per_step": qps * k * 12,
-                "api": "DeviceStore.search -> pvdb_search (one query per call; pinned host query; blocking)",
-            },
-            "gpu_launches": int(launches),
-            "roofline": {
-                "bound": "hbm",
-                "kernel": f"scan_topk_kernel<{args.store_dtype}> (masked GEMV + fused top-k)",
-                "achieved": achieved,
-                "peak": peak,
-                "unit": "GB/s",
-                "frac": achieved / peak,
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes,
-                "us_per_launch": scan_ms * 1e3,
-                "traffic": load_traffic(f"scan_{args.store_dtype}_{args.rows}x{args.dim}") if world == 1 else None,
-            },
-            "clocks": clocks,
+            "config": workload_config(args),
+            "e2e": main["e2e"],
+            "gpu_launches": main["gpu_launches"],
+            "roofline": main["roofline"],
+            "clocks": main["clocks"],
+            "parity_checked": bool(main["parity"]["checked"] and main["parity"]["ok"]),
+            "parity": main["parity"],
+            "fill_seconds": main["fill_seconds"],
         }
+        if "batch" in main:
+            line["batch"] = main["batch"]
+        if c2 is not None:
+            line["c2"] = c2
         if world == 1 and not args.no_cpu_baseline:
+            threads = set_blas_threads()
             per_query, sample, _ = time_oracle(args, args.cpu_queries)
-            line["cpu_baseline"] = {"value": 1.0 / per_query, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+            line["cpu_baseline"] = {"value": 1.0 / per_query, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": sample}
         emit_json(line)
-    store.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -86,7 +86,7 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
   if (prec < PVDB_PREC_F32 || prec > PVDB_PREC_BF16) return fail(PVDB_ERR_INVALID, "search: unknown precision %d", prec);
   if (s->rows == 0) return fill_empty(d_out_scores, d_out_rows, nq * k, st);
 
-  const bool want_rescore = !(flags & PVDB_SEARCH_NO_RESCORE) && has_f32;
+  const bool want_rescore = !(flags & PVDB_SEARCH_NO_RESCORE);
   const bool batch = batch_path_available() && nq >= kBatchMinQueries && !(flags & PVDB_SEARCH_SCAN_ONLY) &&
                      (prec == PVDB_PREC_TF32 || prec == PVDB_PREC_BF16) &&
                      k <= batch_max_k(prec == PVDB_PREC_BF16, want_rescore);

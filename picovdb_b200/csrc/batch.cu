@@ -923,7 +923,8 @@ __global__ void __launch_bounds__(kFinalThreads)
 finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __restrict__ counts,
                       const uint8_t* __restrict__ touched, int n_ctas, int pool_cap, int k_sel, int q_tiles,
                       int64_t nq, int k, const float* __restrict__ qn, int ldq, const float* __restrict__ f32,
-                      int ld32, int rescore, int64_t row_base, float* __restrict__ out_scores,
+                      int ld32, const __nv_bfloat16* __restrict__ b16, int ld16, int rescore, int64_t row_base,
+                      float* __restrict__ out_scores,
                       int64_t* __restrict__ out_rows, const uint64_t* __restrict__ carry_in,
                       uint64_t* __restrict__ carry_out, float* __restrict__ thr_out,
                       const uint32_t* __restrict__ shared_thr, const float* __restrict__ init_thr) {
@@ -1021,22 +1022,41 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
     return;
   }
   if (rescore) {
-    // exact fp32 dot product of the query with each surviving row (one warp per candidate)
+    // exact fp32-accumulated dot product of the fp32 query with each surviving row (one warp per
+    // candidate): against the fp32 matrix when the store keeps one, else against the bf16 mirror --
+    // the same arithmetic as the single-query scan of that store, so a query gets the same answer
+    // alone and inside a batch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float4* q4 = reinterpret_cast<const float4*>(qn + q * ldq);
     for (int cnd = warp; cnd < kept; cnd += kFinalThreads / 32) {
       const uint64_t key = keys[cnd];
       if (key == 0ull) continue;
       const uint32_t row = key_row(key);
-      const float4* v4 = reinterpret_cast<const float4*>(f32 + static_cast<size_t>(row) * ld32);
       float acc = 0.f;
-      for (int i = lane; i < (ld32 >> 2); i += 32) {
-        const float4 a = __ldg(v4 + i);
-        const float4 b = q4[i];
-        acc = fmaf(a.x, b.x, acc);
-        acc = fmaf(a.y, b.y, acc);
-        acc = fmaf(a.z, b.z, acc);
-        acc = fmaf(a.w, b.w, acc);
+      if (f32 != nullptr) {
+        const float4* v4 = reinterpret_cast<const float4*>(f32 + static_cast<size_t>(row) * ld32);
+        for (int i = lane; i < (ld32 >> 2); i += 32) {
+          const float4 a = __ldg(v4 + i);
+          const float4 b = q4[i];
+          acc = fmaf(a.x, b.x, acc);
+          acc = fmaf(a.y, b.y, acc);
+          acc = fmaf(a.z, b.z, acc);
+          acc = fmaf(a.w, b.w, acc);
+        }
+      } else {
+        const uint4* v8 = reinterpret_cast<const uint4*>(b16 + static_cast<size_t>(row) * ld16);
+        for (int i = lane; i < (ld16 >> 3); i += 32) {
+          const uint4 a = __ldg(v8 + i);
+          const float4 b0 = q4[2 * i], b1 = q4[2 * i + 1];
+          acc = fmaf(__uint_as_float(a.x << 16), b0.x, acc);
+          acc = fmaf(__uint_as_float(a.x & 0xffff0000u), b0.y, acc);
+          acc = fmaf(__uint_as_float(a.y << 16), b0.z, acc);
+          acc = fmaf(__uint_as_float(a.y & 0xffff0000u), b0.w, acc);
+          acc = fmaf(__uint_as_float(a.z << 16), b1.x, acc);
+          acc = fmaf(__uint_as_float(a.z & 0xffff0000u), b1.y, acc);
+          acc = fmaf(__uint_as_float(a.w << 16), b1.z, acc);
+          acc = fmaf(__uint_as_float(a.w & 0xffff0000u), b1.w, acc);
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -1211,7 +1231,9 @@ int batch_max_k(bool use_bf16, bool rescore) { return kMaxSel - (rescore ? (use_
 int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq_total,
                  int k, const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows,
                  cudaStream_t st) {
-  const bool rescore = !no_rescore && s->f32.ptr != nullptr;
+  // candidates are always re-scored in fp32 arithmetic unless the caller asks for the raw tensor-core
+  // scores: against the fp32 matrix when there is one, else against the bf16 mirror
+  const bool rescore = !no_rescore;
   const int k_sel = k + (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0);
   if (k_sel > kMaxSel) return fail(PVDB_ERR_UNSUPPORTED, "batch: k=%d too large for the fused tensor-core path", k);
 
@@ -1336,7 +1358,8 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
       }
       finalize_batch_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(
           p.pools, p.counts, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
-          static_cast<const float*>(s->f32.ptr), s->ld_f32, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
+          static_cast<const float*>(s->f32.ptr), s->ld_f32, static_cast<const __nv_bfloat16*>(s->bf16.ptr),
+          s->ld_bf16, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
           d_out_rows + q0 * k, carry_in, carry_out, thr_out, p.shared_thr, thr_in);
       PVDB_LAUNCH_CHECK();
       return PVDB_OK;

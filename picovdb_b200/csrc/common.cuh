@@ -85,6 +85,18 @@ __host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) {
 }
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------- input rounding
+// |x - tf32(x)| when the low 13 mantissa bits are dropped.  Truncation error is an upper bound of the
+// round-to-nearest error of the same value, so a bound built from it holds whichever of the two the
+// tensor core applies to its fp32 operands.
+__device__ __forceinline__ float tf32_trunc_err(float x) {
+  return fabsf(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
+// |x - bf16(x)| for the round-to-nearest-even conversion this library uses for the mirror / queries
+__device__ __forceinline__ float bf16_rn_err(float x) {
+  return fabsf(x - __bfloat162float(__float2bfloat16_rn(x)));
+}
+
 // ---------------------------------------------------------------------------- loads
 // 128-bit streaming load: read-only path, do not allocate in L1 (every byte is used once).
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {

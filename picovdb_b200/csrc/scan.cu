@@ -54,7 +54,8 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
 // (picovdb/pico_vdb.py:584-591).  Output rows are zero padded to ldq floats.
 __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __restrict__ raw, int64_t nq, int dim,
                                                               int already_normalised, float* __restrict__ qn,
-                                                              __nv_bfloat16* __restrict__ qn16, int ldq) {
+                                                              __nv_bfloat16* __restrict__ qn16, int ldq,
+                                                              float* __restrict__ qeps) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -74,19 +75,45 @@ __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __res
       nrm = static_cast<float>(sqrt(d));
       zero = (nrm == 0.f);
     }
+    float e_tf = 0.f, e_bf = 0.f;
     for (int c = lane; c < ldq; c += 32) {
       float y = 0.f;
       if (c < dim) y = zero ? (c == 0 ? 1.f : 0.f) : (already_normalised ? v[c] : __fdiv_rn(v[c], nrm));
       qn[i * ldq + c] = y;
       if (qn16) qn16[i * ldq + c] = __float2bfloat16_rn(y);
+      const float dt = tf32_trunc_err(y), db = bf16_rn_err(y);
+      e_tf = fmaf(dt, dt, e_tf);
+      e_bf = fmaf(db, db, e_bf);
+    }
+    if (qeps != nullptr) {
+      // norm of what the tensor-core operand loses of this query (exactness guard, batch.cu), and the
+      // query's own norm (1 unless the caller passed "normalised" queries that are not)
+      float nn = 0.f;
+      for (int c = lane; c < dim; c += 32) {
+        const float y = qn[i * ldq + c];
+        nn = fmaf(y, y, nn);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        e_tf += __shfl_xor_sync(0xffffffffu, e_tf, o);
+        e_bf += __shfl_xor_sync(0xffffffffu, e_bf, o);
+        nn += __shfl_xor_sync(0xffffffffu, nn, o);
+      }
+      if (lane == 0) {
+        qeps[i * 4 + 0] = sqrtf(e_tf);
+        qeps[i * 4 + 1] = sqrtf(e_bf);
+        qeps[i * 4 + 2] = sqrtf(nn);
+        qeps[i * 4 + 3] = 0.f;
+      }
     }
   }
 }
 
 int launch_prepare_queries(const float* d_raw, int64_t nq, int dim, bool already_normalised, float* d_qn,
-                           __nv_bfloat16* d_qn16, int ldq, cudaStream_t stream) {
+                           __nv_bfloat16* d_qn16, int ldq, float* d_qeps, cudaStream_t stream) {
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((nq + 7) / 8, kNumSMs * 8)));
-  prepare_queries_kernel<<<blocks, 256, 0, stream>>>(d_raw, nq, dim, already_normalised ? 1 : 0, d_qn, d_qn16, ldq);
+  prepare_queries_kernel<<<blocks, 256, 0, stream>>>(d_raw, nq, dim, already_normalised ? 1 : 0, d_qn, d_qn16, ldq,
+                                                     d_qeps);
   PVDB_LAUNCH_CHECK();
   return PVDB_OK;
 }

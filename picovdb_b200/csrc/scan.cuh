@@ -42,9 +42,10 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream);
 int scan_grid_blocks();
 
 // Query preparation (picovdb/pico_vdb.py:584-591): L2-normalise each query in fp32, zero -> e0,
-// write nq x ldq fp32 (zero padded) and optionally a bf16 copy with row stride ldq.
+// write nq x ldq fp32 (zero padded) and optionally a bf16 copy with row stride ldq.  d_qeps (optional,
+// nq x 4 floats): per query ||q - tf32(q)||, ||q - bf16(q)||, ||q|| (the exactness guard's inputs).
 int launch_prepare_queries(const float* d_raw, int64_t nq, int dim, bool already_normalised, float* d_qn,
-                           __nv_bfloat16* d_qn16, int ldq, cudaStream_t stream);
+                           __nv_bfloat16* d_qn16, int ldq, float* d_qeps, cudaStream_t stream);
 
 int launch_merge_topk(const float* d_scores, const int64_t* d_rows, int nlists, int64_t nq, int k,
                       int64_t scores_stride, int64_t rows_stride, float* d_out_scores, int64_t* d_out_rows,

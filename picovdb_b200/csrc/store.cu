@@ -90,28 +90,35 @@ int DeviceBuffer::grow(size_t new_bytes, cudaStream_t stream) {
       va_bytes = want;
       vmm = true;
     }
-    const size_t add = (new_bytes - bytes + gran - 1) / gran * gran;
-    if (bytes + add > va_bytes)
+    const size_t add_total = (new_bytes - bytes + gran - 1) / gran * gran;
+    if (bytes + add_total > va_bytes)
       return fail(PVDB_ERR_OOM, "store buffer would exceed its reserved address range (%zu bytes)", va_bytes);
-    CUmemGenericAllocationHandle h = 0;
-    if (api.create(&h, add, &prop, 0) != CUDA_SUCCESS)
-      return fail(PVDB_ERR_OOM, "cuMemCreate(%zu bytes) failed: out of device memory", add);
-    const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(ptr) + bytes;
-    if (api.map(at, add, 0, h, 0) != CUDA_SUCCESS) {
-      api.release(h);
-      return fail(PVDB_ERR_CUDA, "cuMemMap failed");
+    // physical memory is created in pieces of at most 16 GiB: a 100M x 384 bf16 store on one GPU is a
+    // single 77 GB growth step, and one allocation handle of that size is needlessly hard to place
+    const size_t piece_max = std::max(gran, (size_t(16) << 30) / gran * gran);
+    for (size_t done = 0; done < add_total;) {
+      const size_t add = std::min(piece_max, add_total - done);
+      CUmemGenericAllocationHandle h = 0;
+      if (api.create(&h, add, &prop, 0) != CUDA_SUCCESS)
+        return fail(PVDB_ERR_OOM, "cuMemCreate(%zu bytes) failed: out of device memory", add);
+      const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(ptr) + bytes;
+      if (api.map(at, add, 0, h, 0) != CUDA_SUCCESS) {
+        api.release(h);
+        return fail(PVDB_ERR_CUDA, "cuMemMap failed");
+      }
+      CUmemAccessDesc acc{};
+      acc.location = prop.location;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      if (api.set_access(at, add, &acc, 1) != CUDA_SUCCESS) {
+        api.unmap(at, add);
+        api.release(h);
+        return fail(PVDB_ERR_CUDA, "cuMemSetAccess failed");
+      }
+      chunks.push_back({static_cast<unsigned long long>(h), bytes, add});
+      PVDB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(at), 0, add, stream));
+      bytes += add;
+      done += add;
     }
-    CUmemAccessDesc acc{};
-    acc.location = prop.location;
-    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    if (api.set_access(at, add, &acc, 1) != CUDA_SUCCESS) {
-      api.unmap(at, add);
-      api.release(h);
-      return fail(PVDB_ERR_CUDA, "cuMemSetAccess failed");
-    }
-    chunks.push_back({static_cast<unsigned long long>(h), bytes, add});
-    PVDB_CUDA(cudaMemsetAsync(reinterpret_cast<void*>(at), 0, add, stream));
-    bytes += add;
     return PVDB_OK;
   }
   // plain allocation (no VMM support): allocate, copy, free
@@ -176,7 +183,7 @@ void Scratch::release() {
 __global__ void __launch_bounds__(256) upsert_normalize_scatter_kernel(
     const float* __restrict__ src, const int64_t* __restrict__ rows, int64_t row0, int64_t n, int dim,
     float* __restrict__ f32, int ld32, __nv_bfloat16* __restrict__ b16, int ld16,
-    uint32_t* __restrict__ active) {
+    uint32_t* __restrict__ active, uint32_t* __restrict__ err_words) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -194,11 +201,27 @@ __global__ void __launch_bounds__(256) upsert_normalize_scatter_kernel(
     const float nrm = static_cast<float>(sqrt(d));
     const bool zero = (nrm == 0.f);
     const int64_t row = rows ? rows[i] : row0 + i;
+    float e_tf = 0.f, e_bf = 0.f;  // squared input-rounding error of this row (exactness guard)
     for (int c = lane; c < ldmax; c += 32) {
       float y = 0.f;
       if (c < dim) y = zero ? (c == 0 ? 1.f : 0.f) : __fdiv_rn(v[c], nrm);
       if (f32 != nullptr && c < ld32) f32[row * ld32 + c] = y;
       if (b16 != nullptr && c < ld16) b16[row * ld16 + c] = __float2bfloat16_rn(y);
+      const float dt = tf32_trunc_err(y), db = bf16_rn_err(y);
+      e_tf = fmaf(dt, dt, e_tf);
+      e_bf = fmaf(db, db, e_bf);
+    }
+    if (err_words != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        e_tf += __shfl_xor_sync(0xffffffffu, e_tf, o);
+        e_bf += __shfl_xor_sync(0xffffffffu, e_bf, o);
+      }
+      if (lane == 0) {
+        // non-negative floats order like their bit patterns
+        if (__float_as_uint(e_tf) > err_words[0]) atomicMax(&err_words[0], __float_as_uint(e_tf));
+        if (__float_as_uint(e_bf) > err_words[1]) atomicMax(&err_words[1], __float_as_uint(e_bf));
+      }
     }
     if (lane == 0) atomicOr(&active[row >> 5], 1u << (row & 31));
   }
@@ -251,6 +274,33 @@ __global__ void __launch_bounds__(256) mirror_rows_kernel(const float* __restric
       float y = 0.f;
       if (c < dim) y = src_dense ? src_dense[i * dim + c] : f32[row * ld32 + c];
       b16[row * ld16 + c] = __float2bfloat16_rn(y);
+    }
+  }
+}
+
+// Raw uploads bypass the upsert kernel: same rounding-error bookkeeping for rows [row0, row0+n).
+__global__ void __launch_bounds__(256) row_error_kernel(const float* __restrict__ f32, int ld32, int dim,
+                                                        int64_t row0, int64_t n, uint32_t* __restrict__ err_words) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t i = warp; i < n; i += nwarps) {
+    const float* v = f32 + (row0 + i) * ld32;
+    float e_tf = 0.f, e_bf = 0.f;
+    for (int c = lane; c < dim; c += 32) {
+      const float y = v[c];
+      const float dt = tf32_trunc_err(y), db = bf16_rn_err(y);
+      e_tf = fmaf(dt, dt, e_tf);
+      e_bf = fmaf(db, db, e_bf);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e_tf += __shfl_xor_sync(0xffffffffu, e_tf, o);
+      e_bf += __shfl_xor_sync(0xffffffffu, e_bf, o);
+    }
+    if (lane == 0) {
+      if (__float_as_uint(e_tf) > err_words[0]) atomicMax(&err_words[0], __float_as_uint(e_tf));
+      if (__float_as_uint(e_bf) > err_words[1]) atomicMax(&err_words[1], __float_as_uint(e_bf));
     }
   }
 }
@@ -383,7 +433,10 @@ extern "C" int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_
   s->ldq = (dim + 63) & ~63;  // whole K boxes of the batch path's TMA loads (32 fp32 / 64 bf16), zero padded
   s->flags = flags;
   s->h_pinned.pinned_host = true;
+  s->h_flag.pinned_host = true;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_err_words), 16);
+  if (e == cudaSuccess) e = cudaMemset(s->d_err_words, 0, 16);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->order_event, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     delete s;
@@ -414,8 +467,9 @@ extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
   s->active.release();
   s->drop_columns();
   for (Scratch* sc : {&s->d_in, &s->d_rows, &s->d_prefilter, &s->d_qn, &s->d_qn16, &s->d_partial, &s->d_out,
-                      &s->d_misc, &s->h_pinned})
+                      &s->d_misc, &s->h_pinned, &s->d_qeps, &s->d_flag, &s->h_flag})
     sc->release();
+  if (s->d_err_words) cudaFree(s->d_err_words);
   if (s->order_event) cudaEventDestroy(s->order_event);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -474,7 +528,8 @@ static int upsert_device(pvdb_store* s, const float* d_vecs, const int64_t* d_ro
   PVDB_TRY(s->ensure_capacity(max_row + 1, st));
   upsert_normalize_scatter_kernel<<<warp_grid(n), 256, 0, st>>>(
       d_vecs, d_rows, row0, n, s->dim, static_cast<float*>(s->f32.ptr), s->ld_f32,
-      static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16, static_cast<uint32_t*>(s->active.ptr));
+      static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16, static_cast<uint32_t*>(s->active.ptr),
+      s->f32.ptr ? s->d_err_words : nullptr);
   PVDB_LAUNCH_CHECK();
   s->rows = std::max(s->rows, max_row + 1);
   return PVDB_OK;
@@ -655,6 +710,11 @@ extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const
     if (s->bf16.ptr) {
       mirror_rows_kernel<<<warp_grid(m), 256, 0, st>>>(dense, s->dim, static_cast<const float*>(s->f32.ptr), s->ld_f32,
                                                        static_cast<__nv_bfloat16*>(s->bf16.ptr), s->ld_bf16, row0 + i0, m);
+      PVDB_LAUNCH_CHECK();
+    }
+    if (s->f32.ptr) {
+      row_error_kernel<<<warp_grid(m), 256, 0, st>>>(static_cast<const float*>(s->f32.ptr), s->ld_f32, s->dim,
+                                                     row0 + i0, m, s->d_err_words);
       PVDB_LAUNCH_CHECK();
     }
   }

@@ -79,6 +79,15 @@ struct pvdb_store {
   pvdb::Scratch d_out;      // results before the D2H copy
   pvdb::Scratch d_misc;
   pvdb::Scratch h_pinned;   // pinned bounce buffer for results
+  pvdb::Scratch d_qeps;     // per query: ||q - tf32(q)||, ||q - bf16(q)|| (exactness guard of the tensor paths)
+  pvdb::Scratch d_flag;     // guard: [count][flagged query indices]
+  pvdb::Scratch h_flag;     // pinned copy of d_flag
+  // Largest input-rounding error over the rows ever written, as the uint image of two non-negative
+  // floats: [0] = max_r ||v_r - tf32_trunc(v_r)||^2, [1] = max_r ||v_r - bf16_rn(v_r)||^2.  Only
+  // maintained when the store keeps the fp32 matrix (otherwise the bf16 rows ARE the exact data).
+  uint32_t* d_err_words = nullptr;
+  int64_t guard_flagged_last = 0;   // queries of the last search that fell back to the exact scan
+  int64_t guard_flagged_total = 0;
   uint64_t partial_gen_inited = 0;  // d_partial.gen whose control words have been zeroed
 
   // Make `s` the stream the store's data is ordered on (inserts an event edge when it changes).
