@@ -54,6 +54,7 @@ extern "C" {
 #define PVDB_SEARCH_QUERIES_NORMALIZED 0x100 /* skip the query L2-normalisation (pico_vdb.py:584-591) */
 #define PVDB_SEARCH_NO_RESCORE 0x200         /* tensor-core paths: return the low-precision scores */
 #define PVDB_SEARCH_SCAN_ONLY 0x400          /* answer every query with its own HBM scan pass (no batching) */
+#define PVDB_SEARCH_NO_GUARD 0x800           /* tensor-core paths: skip the exactness guard (see pvdb_search) */
 
 typedef struct pvdb_store pvdb_store_t;
 
@@ -141,6 +142,16 @@ int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t nq, int k, 
  * set, and write the k best as out_scores[nq*k] / out_rows[nq*k]. */
 int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,
                 const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows);
+/* Exactness of the tensor-core precisions (TF32 / BF16 batches).  The tensor-core pass only RANKS
+ * rows; the best k + slack are re-scored with the exact arithmetic of the single-query scan.  A
+ * guard then proves, per query, that no row outside the kept candidates can belong to the top k
+ * (re-scored k-th best > weakest kept low-precision score + input-rounding bound for unit vectors).
+ * Queries that cannot be proven (dense near-ties, e.g. near-duplicate corpora) are answered again by
+ * the exact scan, so a query returns the same ids alone and inside a batch -- the id rule of the
+ * reference's numpy path (pico_vdb.py:699-714).  The guard costs one stream synchronisation per
+ * call (also in pvdb_search_dev); PVDB_SEARCH_NO_GUARD skips it.  This call reports how many queries
+ * of the last search on this store / of all searches fell back to the exact scan. */
+int pvdb_store_guard_stats(pvdb_store_t* s, int64_t* out_last, int64_t* out_total);
 int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
                     const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
                     int64_t* d_out_rows, void* stream);

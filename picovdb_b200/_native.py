@@ -27,6 +27,7 @@ PREC_AUTO, PREC_F32, PREC_TF32, PREC_BF16 = 0, 1, 2, 3
 SEARCH_QUERIES_NORMALIZED = 0x100
 SEARCH_NO_RESCORE = 0x200
 SEARCH_SCAN_ONLY = 0x400
+SEARCH_NO_GUARD = 0x800
 
 PRECISIONS = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 
@@ -85,6 +86,7 @@ SIGNATURES = {
     "pvdb_store_column_write": (C.c_int, [_P, C.c_int, _P, _I64, _P, _I64]),
     "pvdb_store_column_drop": (C.c_int, [_P, C.c_int]),
     "pvdb_search_dev": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "pvdb_store_guard_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
     "pvdb_merge_topk_dev": (C.c_int, [C.c_int, _P, _P, C.c_int, _I64, C.c_int, _I64, _I64, _P, _P, _P]),
     "pvdb_kernel_launches": (_I64, []),
 }

@@ -92,9 +92,18 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
                      k <= batch_max_k(prec == PVDB_PREC_BF16, want_rescore);
   const bool normalised = (flags & PVDB_SEARCH_QUERIES_NORMALIZED) != 0;
   const bool need16 = batch && (prec == PVDB_PREC_BF16);
+  // exactness guard of the tensor-core paths (batch.cu): on unless the caller opts out or asks for
+  // the raw low-precision scores
+  const bool guard = batch && want_rescore && !(flags & PVDB_SEARCH_NO_GUARD);
+  s->guard_flagged_last = 0;
   const float* d_qn = nullptr;
   __nv_bfloat16* d_qn16 = nullptr;
-  if (normalised && s->ldq == s->dim && !need16 && (!batch || nq == batch_query_rows(nq))) {
+  float* d_qeps = nullptr;
+  if (guard) {
+    PVDB_TRY(s->d_qeps.ensure(static_cast<size_t>(nq) * 4 * sizeof(float)));
+    d_qeps = static_cast<float*>(s->d_qeps.ptr);
+  }
+  if (normalised && s->ldq == s->dim && !need16 && !guard && (!batch || nq == batch_query_rows(nq))) {
     d_qn = d_queries;  // already in the padded layout the kernels read: no preparation launch at all
   } else if (!batch && !normalised) {
     d_qn = nullptr;    // the scan kernel normalises the raw query itself (fused, no extra launch)
@@ -115,13 +124,48 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
                                   static_cast<size_t>(nq_pad - nq) * s->ldq * sizeof(__nv_bfloat16), st));
     }
     PVDB_TRY(launch_prepare_queries(d_queries, nq, s->dim, normalised, static_cast<float*>(s->d_qn.ptr), d_qn16,
-                                    s->ldq, st));
+                                    s->ldq, d_qeps, st));
     d_qn = static_cast<const float*>(s->d_qn.ptr);
   }
 
   if (batch) {
-    return search_batch(s, prec == PVDB_PREC_BF16, d_qn, d_qn16, nq, k, d_pref, (flags & PVDB_SEARCH_NO_RESCORE) != 0,
-                        d_out_scores, d_out_rows, st);
+    unsigned* d_flag_count = nullptr;
+    int* d_flag_list = nullptr;
+    if (guard) {
+      PVDB_TRY(s->d_flag.ensure((static_cast<size_t>(nq) + 4) * sizeof(int)));
+      PVDB_TRY(s->h_flag.ensure((static_cast<size_t>(nq) + 4) * sizeof(int)));
+      d_flag_count = static_cast<unsigned*>(s->d_flag.ptr);
+      d_flag_list = static_cast<int*>(s->d_flag.ptr) + 4;
+      PVDB_CUDA(cudaMemsetAsync(d_flag_count, 0, sizeof(unsigned), st));
+    }
+    PVDB_TRY(search_batch(s, prec == PVDB_PREC_BF16, d_qn, d_qn16, nq, k, d_pref, !want_rescore, d_qeps, d_flag_count,
+                          d_flag_list, d_out_scores, d_out_rows, st));
+    if (!guard) return PVDB_OK;
+    // The one host round trip of a guarded tensor-core search: how many queries could not be PROVEN
+    // exact?  (Normally none; near-duplicate corpora flag many.)  Those are answered again by the
+    // exact scan of the same store -- fp32 rows when the store has them, else the bf16 rows -- which
+    // overwrites their slice of the output.
+    int* h = static_cast<int*>(s->h_flag.ptr);
+    PVDB_CUDA(cudaMemcpyAsync(h, d_flag_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    PVDB_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_flag = std::min<int64_t>(static_cast<unsigned>(h[0]), nq);
+    s->guard_flagged_last = n_flag;
+    s->guard_flagged_total += n_flag;
+    if (n_flag == 0) return PVDB_OK;
+    PVDB_CUDA(cudaMemcpyAsync(h + 4, d_flag_list, static_cast<size_t>(n_flag) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    PVDB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t i = 0; i < n_flag; ++i) {
+      const int64_t q = h[4 + i];
+      if (q < 0 || q >= nq) return fail(PVDB_ERR_CUDA, "guard: corrupt flag list");
+      // exactly the call a lone query takes: raw query normalised inside the scan kernel
+      if (normalised)
+        PVDB_TRY(search_scan(s, !has_f32, d_qn + q * s->ldq, nullptr, 1, k, d_pref, d_out_scores + q * k,
+                             d_out_rows + q * k, st));
+      else
+        PVDB_TRY(search_scan(s, !has_f32, nullptr, d_queries + q * s->dim, 1, k, d_pref, d_out_scores + q * k,
+                             d_out_rows + q * k, st));
+    }
+    return PVDB_OK;
   }
   // scan path: TF32 requests with few queries are served by the exact fp32 scan
   return search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st);
@@ -221,6 +265,13 @@ extern "C" int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t 
   std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
   std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
   if (out_candidates) *out_candidates = static_cast<int64_t>(*h_count);
+  return PVDB_OK;
+}
+
+extern "C" int pvdb_store_guard_stats(pvdb_store_t* s, int64_t* out_last, int64_t* out_total) {
+  PVDB_ENTER(s);
+  if (out_last) *out_last = s->guard_flagged_last;
+  if (out_total) *out_total = s->guard_flagged_total;
   return PVDB_OK;
 }
 

@@ -68,8 +68,13 @@ constexpr int kEpiThreads = 128 * kEpiHalves;
 constexpr int kBatchThreads = 128 + kEpiThreads;
 constexpr int kTmemCols = 512;      // two fp32 accumulators of 256 columns
 constexpr int kMaxSel = 160;        // largest k_sel (a pool of 256 keeps two 32-column chunks of headroom + 32 slots)
-constexpr int kSlackTF32 = 32;      // extra candidates kept for fp32 re-scoring (tf32 ranking noise)
-constexpr int kSlackBF16 = 54;      // bf16 ranking noise is ~8x larger
+// Extra candidates kept for the exact re-scoring.  The exactness guard (finalize) accepts a query only
+// when the re-scored k-th best beats the weakest kept candidate by more than the input-rounding bound,
+// so the slack must span that bound in score space.  The spacing of scores at rank r shrinks like
+// 1 / r: small k gets by with 32 (tf32) / 54 (bf16); large k takes what the pool allows (k_sel <= 160).
+constexpr int kSlackTF32 = 32;
+constexpr int kSlackBF16 = 54;
+constexpr int kSlackLargeK = 60;
 constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
 // The pair (cta_group::2) variant is validated (all batch tests pass with PVDB_BATCH_PAIR=1) but measured
 // SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
@@ -838,6 +843,24 @@ __device__ __forceinline__ void warp_find_bin_desc(const unsigned* hist, int kk,
 constexpr int kFinalThreads = 256;
 constexpr int kFinalCap = 4096;  // keys held in shared memory (32 KB)
 
+// Exactness guard (final merge only).  The tensor-core pass ranks rows by a LOW-PRECISION score
+// lowp(r) whose distance to the exact fp32 score is bounded for unit vectors by the input rounding:
+//   |exact(r) - lowp(r)| <= ||q - round(q)|| * ||v_r|| + ||round(q)|| * ||v_r - round(v_r)|| + accumulation
+// (Cauchy-Schwarz on each operand's rounding error).  Every row that is NOT among the k_sel kept
+// candidates has lowp <= L, the k_sel-th best low-precision score, hence exact <= L + eps.  If the
+// re-scored k-th best candidate is strictly above L + eps, no outside row can enter the top k and the
+// result equals the exact scan's.  Otherwise the query is FLAGGED and re-run on the exact scan path
+// (api.cu).  eps uses the query's measured rounding norm and the store's tracked worst row.
+struct GuardParams {
+  int mode;                   // 0 off; 1 tf32 pass / fp32 rows; 2 bf16 pass / fp32 rows; 3 bf16 pass / bf16-only store
+  const float* qeps;          // [nq][4]: ||q - tf32(q)||, ||q - bf16(q)||, ||q||
+  const uint32_t* err_words;  // store: max ||v - tf32(v)||^2, max ||v - bf16(v)||^2 (float bits)
+  float acc_slop;             // accumulation-order allowance
+  unsigned* flag_count;       // flagged queries: count and list (indices into the whole call's batch)
+  int* flag_list;
+  int64_t q_offset;
+};
+
 __device__ __forceinline__ void block_sort_desc(uint64_t* keys, int n_pow2) {
   for (int size = 2; size <= n_pow2; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -927,7 +950,8 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
                       float* __restrict__ out_scores,
                       int64_t* __restrict__ out_rows, const uint64_t* __restrict__ carry_in,
                       uint64_t* __restrict__ carry_out, float* __restrict__ thr_out,
-                      const uint32_t* __restrict__ shared_thr, const float* __restrict__ init_thr) {
+                      const uint32_t* __restrict__ shared_thr, const float* __restrict__ init_thr,
+                      const GuardParams guard) {
   __shared__ uint64_t keys[kFinalCap];
   __shared__ int s_lists[kNumSMs];
   __shared__ int s_nlists;
@@ -1021,6 +1045,12 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
     }
     return;
   }
+  // weakest kept candidate's low-precision score: rows outside the list score no more than this
+  // (an empty k_sel-th slot means every eligible row is in the list: nothing outside)
+  const uint64_t weakest = n_keys >= k_sel ? keys[k_sel - 1] : 0ull;
+  const bool have_outside = weakest != 0ull;
+  const float lowp_bound = have_outside ? key_score(weakest) : -INFINITY;
+  __syncthreads();  // everybody has read the low-precision key before re-scoring overwrites it
   if (rescore) {
     // exact fp32-accumulated dot product of the fp32 query with each surviving row (one warp per
     // candidate): against the fp32 matrix when the store keeps one, else against the bf16 mirror --
@@ -1063,6 +1093,17 @@ finalize_batch_kernel(const uint64_t* __restrict__ pools, const uint16_t* __rest
       if (lane == 0) keys[cnd] = make_key(acc, row);
     }
     block_sort_prefix(keys, kept);
+    if (guard.mode != 0 && threadIdx.x == 0 && have_outside && kept >= k) {
+      const float* e = guard.qeps + q * 4;
+      const float qn_norm = fmaxf(e[2], 1.f);
+      const float ev_tf = sqrtf(__uint_as_float(guard.err_words[0])), ev_bf = sqrtf(__uint_as_float(guard.err_words[1]));
+      float eps = guard.acc_slop;
+      if (guard.mode == 1) eps += e[0] * 1.0001f + qn_norm * ev_tf * 1.0001f;   // rows have unit norm
+      else if (guard.mode == 2) eps += e[1] * 1.0001f + qn_norm * ev_bf * 1.0001f;
+      else eps += e[1] * 1.0001f;                                              // the stored rows are exact
+      const float exact_kth = key_score(keys[k - 1]);
+      if (!(exact_kth > lowp_bound + eps)) guard.flag_list[atomicAdd(guard.flag_count, 1u)] = static_cast<int>(guard.q_offset + q);
+    }
   }
   for (int j = threadIdx.x; j < k; j += blockDim.x) {
     const uint64_t key = (j < kept) ? keys[j] : 0ull;
@@ -1191,12 +1232,17 @@ static void batch_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at
 // cluster must fit a GPC, so sizes above 2 may leave a few SMs unused).  The static visit schedule
 // needs every unit resident, so the grid never exceeds this.
 static int batch_max_units(const void* kern, int cl, int* out) {
+  // Function attributes and occupancy belong to a (device, kernel) pair: a process that opens stores
+  // on two GPUs must opt each device into the large dynamic shared memory separately.
+  struct Entry { int device; const void* kern; int units; };
   static std::mutex mu;
-  static std::vector<std::pair<const void*, int>> cache;
+  static std::vector<Entry> cache;
+  int device = 0;
+  PVDB_CUDA(cudaGetDevice(&device));
   std::lock_guard<std::mutex> g(mu);
   for (auto& e : cache)
-    if (e.first == kern) {
-      *out = e.second;
+    if (e.device == device && e.kern == kern) {
+      *out = e.units;
       return PVDB_OK;
     }
   PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmem)));
@@ -1208,7 +1254,7 @@ static int batch_max_units(const void* kern, int cl, int* out) {
   PVDB_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
   if (n < 1) return fail(PVDB_ERR_CUDA, "batch: the device cannot hold one cluster of %d CTAs", cl);
   n = std::min(n, kNumSMs / cl);
-  cache.emplace_back(kern, n);
+  cache.push_back({device, kern, n});
   *out = n;
   return PVDB_OK;
 }
@@ -1226,15 +1272,23 @@ static int launch_batch(const void* kern, int cl, const CUtensorMap& mq, const C
 
 int64_t batch_query_rows(int64_t nq) { return (nq + kBM - 1) / kBM * kBM; }
 
+// candidates kept per query for a top-k request
+static int batch_k_sel(int k, bool use_bf16, bool rescore) {
+  if (!rescore) return k;
+  const int base = use_bf16 ? kSlackBF16 : kSlackTF32;
+  const int slack = k <= 32 ? base : std::max(base, std::min(kSlackLargeK, kMaxSel - k));
+  return k + slack;
+}
+
 int batch_max_k(bool use_bf16, bool rescore) { return kMaxSel - (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0); }
 
 int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq_total,
-                 int k, const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows,
-                 cudaStream_t st) {
+                 int k, const uint32_t* d_pref, bool no_rescore, const float* d_qeps, unsigned* d_flag_count,
+                 int* d_flag_list, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
   // candidates are always re-scored in fp32 arithmetic unless the caller asks for the raw tensor-core
   // scores: against the fp32 matrix when there is one, else against the bf16 mirror
   const bool rescore = !no_rescore;
-  const int k_sel = k + (rescore ? (use_bf16 ? kSlackBF16 : kSlackTF32) : 0);
+  const int k_sel = batch_k_sel(k, use_bf16, rescore);
   if (k_sel > kMaxSel) return fail(PVDB_ERR_UNSUPPORTED, "batch: k=%d too large for the fused tensor-core path", k);
 
   // Two query tiles or more: 2-CTA clusters share every database tile through TMA multicast (each
@@ -1256,6 +1310,18 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   const int total_tiles = static_cast<int>((s->rows + kBN - 1) / kBN);
   for (int64_t q0 = 0; q0 < nq_total; q0 += max_q) {
     const int64_t nq = std::min(max_q, nq_total - q0);
+    GuardParams guard{};
+    if (rescore && d_qeps != nullptr) {
+      guard.mode = !use_bf16 ? 1 : (s->f32.ptr != nullptr ? 2 : 3);
+      guard.qeps = d_qeps + q0 * 4;
+      guard.err_words = s->d_err_words;
+      // fp32 accumulation inside the tensor core (one rounding per K step of 8 / 16 elements, |partial
+      // sums| <= 1) plus the re-scoring's own summation order: a generous (dim / 4 + 16) ulps of 1
+      guard.acc_slop = (static_cast<float>(s->dim) / 4.f + 16.f) * 1.1920929e-7f;
+      guard.flag_count = d_flag_count;
+      guard.flag_list = d_flag_list;
+      guard.q_offset = q0;
+    }
     BatchParams p{};
     p.nq = nq;
     p.n_rows = s->rows;
@@ -1360,7 +1426,8 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
           p.pools, p.counts, p.touched, grid, p.pool_cap, p.k_sel, p.q_tiles, nq, k, d_qn + q0 * s->ldq, s->ldq,
           static_cast<const float*>(s->f32.ptr), s->ld_f32, static_cast<const __nv_bfloat16*>(s->bf16.ptr),
           s->ld_bf16, rescore ? 1 : 0, s->row_base, d_out_scores + q0 * k,
-          d_out_rows + q0 * k, carry_in, carry_out, thr_out, p.shared_thr, thr_in);
+          d_out_rows + q0 * k, carry_in, carry_out, thr_out, p.shared_thr, thr_in,
+          carry_out == nullptr ? guard : GuardParams{});
       PVDB_LAUNCH_CHECK();
       return PVDB_OK;
     };

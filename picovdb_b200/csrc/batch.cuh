@@ -18,8 +18,10 @@ int64_t batch_query_rows(int64_t nq);
 int batch_max_k(bool use_bf16, bool rescore);
 
 // d_qn: nq x ldq normalised fp32 queries; d_qn16: the same in bf16 (only for use_bf16).
+// d_qeps / d_flag_count / d_flag_list: exactness guard (see GuardParams in batch.cu); d_qeps == NULL
+// switches it off.  Flagged queries are appended to d_flag_list (the caller zeroes *d_flag_count).
 int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfloat16* d_qn16, int64_t nq, int k,
-                 const uint32_t* d_pref, bool no_rescore, float* d_out_scores, int64_t* d_out_rows,
-                 cudaStream_t st);
+                 const uint32_t* d_pref, bool no_rescore, const float* d_qeps, unsigned* d_flag_count,
+                 int* d_flag_list, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st);
 
 }  // namespace pvdb

@@ -94,21 +94,25 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     // Fused query preparation (picovdb/pico_vdb.py:584-591): every block normalises the raw query
     // itself -- fp32 sum of squares, fp32 norm, IEEE division, zero query -> e0 -- which saves a
     // kernel launch and a round trip through HBM on the single-query path.
-    __shared__ float s_part[kScanWarps];
-    float ss = 0.f;
-    for (int i = tid; i < p.query_floats; i += kScanThreads) {
-      const float x = (i < p.dim) ? p.raw_query[i] : 0.f;
-      sq[i] = x;
-      ss = fmaf(x, x, ss);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    if (lane == 0) s_part[warp] = ss;
+    // The sum of squares is formed exactly like prepare_queries_kernel and the upsert kernel form it
+    // (lane-strided fp32 partial sums of ONE warp, fp64 butterfly), so a query is normalised to the
+    // same bits whether it arrives alone or inside a batch.
+    __shared__ float s_nrm;
+    for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = (i < p.dim) ? p.raw_query[i] : 0.f;
     __syncthreads();
-    double tot = 0.0;
+    if (warp == 0) {
+      float ss = 0.f;
+      for (int c = lane; c < p.dim; c += 32) {
+        const float x = sq[c];
+        ss = fmaf(x, x, ss);
+      }
+      double d = static_cast<double>(ss);
 #pragma unroll
-    for (int w2 = 0; w2 < kScanWarps; ++w2) tot += static_cast<double>(s_part[w2]);
-    const float nrm = static_cast<float>(sqrt(tot));
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0) s_nrm = static_cast<float>(sqrt(d));
+    }
+    __syncthreads();
+    const float nrm = s_nrm;
     for (int i = tid; i < p.query_floats; i += kScanThreads) {
       const float x = sq[i];
       sq[i] = (nrm == 0.f) ? (i == 0 ? 1.f : 0.f) : __fdiv_rn(x, nrm);

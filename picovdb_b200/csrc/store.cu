@@ -333,19 +333,17 @@ __global__ void popcount_kernel(const uint32_t* __restrict__ words, int64_t nwor
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// new row i := old row keep[i] for both matrices
-__global__ void __launch_bounds__(256) compact_rows_kernel(const int64_t* __restrict__ keep, int64_t n,
-                                                           const float* __restrict__ f32_old,
-                                                           float* __restrict__ f32_new, int ld32,
-                                                           const __nv_bfloat16* __restrict__ b16_old,
-                                                           __nv_bfloat16* __restrict__ b16_new, int ld16) {
+// scratch row i := matrix row keep[i]; rows are `row_u4` 16-byte units long (both matrices keep
+// 16-byte aligned row strides), so one kernel serves the fp32 matrix and the bf16 mirror
+__global__ void __launch_bounds__(256) compact_gather_kernel(const int64_t* __restrict__ keep, int64_t n,
+                                                             const uint4* __restrict__ src, int row_u4,
+                                                             uint4* __restrict__ dst) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t i = warp; i < n; i += nwarps) {
-    const int64_t src = keep[i];
-    if (f32_old) for (int c = lane; c < ld32; c += 32) f32_new[i * ld32 + c] = f32_old[src * ld32 + c];
-    if (b16_old) for (int c = lane; c < ld16; c += 32) b16_new[i * ld16 + c] = b16_old[src * ld16 + c];
+    const uint4* s = src + keep[i] * row_u4;
+    for (int c = lane; c < row_u4; c += 32) dst[i * row_u4 + c] = s[c];
   }
 }
 
@@ -756,22 +754,43 @@ extern "C" int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int
   }
   cudaStream_t st = s->stream;
   PVDB_TRY(s->use_stream(st));
-  DeviceBuffer nf32, nb16;
-  if (s->capacity > 0) {
-    if (s->f32.ptr) PVDB_TRY(nf32.grow(s->f32.bytes, st));
-    if (s->bf16.ptr) {
-      int rc = nb16.grow(s->bf16.bytes, st);
-      if (rc != PVDB_OK) { nf32.release(); return rc; }
-    }
-  }
+  // In place, block by block: keep_rows is strictly ascending, so keep[i] >= i -- a block of new rows
+  // [a, b) only reads old rows >= a, and once it has been staged in scratch and written back, later
+  // blocks read old rows >= b, which no earlier write touched.  No second copy of the matrices (the
+  // first version allocated one: 2x the store's HBM, impossible for a C5-sized shard).
   if (n > 0) {
     PVDB_TRY(s->d_rows.ensure(static_cast<size_t>(n) * sizeof(int64_t)));
     PVDB_CUDA(cudaMemcpyAsync(s->d_rows.ptr, keep_rows, static_cast<size_t>(n) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    compact_rows_kernel<<<warp_grid(n), 256, 0, st>>>(
-        static_cast<const int64_t*>(s->d_rows.ptr), n, static_cast<const float*>(s->f32.ptr),
-        static_cast<float*>(nf32.ptr), s->ld_f32, static_cast<const __nv_bfloat16*>(s->bf16.ptr),
-        static_cast<__nv_bfloat16*>(nb16.ptr), s->ld_bf16);
-    PVDB_LAUNCH_CHECK();
+    const int64_t* d_keep = static_cast<const int64_t*>(s->d_rows.ptr);
+    struct Mat { void* ptr; size_t row_bytes; };
+    const Mat mats[2] = {{s->f32.ptr, static_cast<size_t>(s->ld_f32) * sizeof(float)},
+                         {s->bf16.ptr, static_cast<size_t>(s->ld_bf16) * sizeof(__nv_bfloat16)}};
+    for (const Mat& m : mats) {
+      if (m.ptr == nullptr) continue;
+      const int64_t chunk = std::max<int64_t>(1, kStageBytes / static_cast<int64_t>(m.row_bytes));
+      PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * m.row_bytes));
+      // leading rows that stay where they are need no copy at all
+      int64_t first = 0;
+      while (first < n && keep_rows[first] == first) ++first;
+      for (int64_t i0 = first; i0 < n; i0 += chunk) {
+        const int64_t cnt = std::min(chunk, n - i0);
+        compact_gather_kernel<<<warp_grid(cnt), 256, 0, st>>>(d_keep + i0, cnt, static_cast<const uint4*>(m.ptr),
+                                                              static_cast<int>(m.row_bytes / 16),
+                                                              static_cast<uint4*>(s->d_in.ptr));
+        PVDB_LAUNCH_CHECK();
+        PVDB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(m.ptr) + static_cast<size_t>(i0) * m.row_bytes,
+                                  s->d_in.ptr, static_cast<size_t>(cnt) * m.row_bytes, cudaMemcpyDeviceToDevice, st));
+      }
+      // rows past the new end read as zeros again (deleted-row convention, pico_vdb.py:523)
+      if (s->rows > n)
+        PVDB_CUDA(cudaMemsetAsync(static_cast<unsigned char*>(m.ptr) + static_cast<size_t>(n) * m.row_bytes, 0,
+                                  static_cast<size_t>(s->rows - n) * m.row_bytes, st));
+    }
+  } else {
+    if (s->f32.ptr && s->rows > 0)
+      PVDB_CUDA(cudaMemsetAsync(s->f32.ptr, 0, static_cast<size_t>(s->rows) * s->ld_f32 * sizeof(float), st));
+    if (s->bf16.ptr && s->rows > 0)
+      PVDB_CUDA(cudaMemsetAsync(s->bf16.ptr, 0, static_cast<size_t>(s->rows) * s->ld_bf16 * sizeof(__nv_bfloat16), st));
   }
   if (s->active.ptr) {
     PVDB_CUDA(cudaMemsetAsync(s->active.ptr, 0, s->active.bytes, st));
@@ -783,10 +802,6 @@ extern "C" int pvdb_store_compact(pvdb_store_t* s, const int64_t* keep_rows, int
     }
   }
   PVDB_CUDA(cudaStreamSynchronize(st));
-  std::swap(s->f32, nf32);
-  std::swap(s->bf16, nb16);
-  nf32.release();
-  nb16.release();
   s->drop_columns();  // row numbers changed: the host re-uploads the columns it still needs
   s->rows = n;
   return PVDB_OK;

@@ -168,14 +168,21 @@ class _ColumnIndex:
                 self.set(row, doc)
 
     def _code(self, value: Any, create: bool) -> int:
+        """Dictionary code of a STORED value (create=True) or of a filter value (create=False).  An
+        unhashable stored value disables the column for good (the key falls back to the Python loop);
+        an unhashable FILTER value only makes that one query unsupported (TypeError propagates to the
+        caller) -- it says nothing about the stored data."""
+        if not create:
+            code = self.vocab.get(value)  # raises TypeError for an unhashable filter value
+            return -1 if code is None else code
         try:
             code = self.vocab.get(value)
-            if code is None and create:
+            if code is None:
                 code = self.vocab[value] = len(self.vocab)
-        except TypeError:  # unhashable metadata value: this key falls back to the Python loop
+        except TypeError:
             self.ok = False
             return -1
-        return -1 if code is None else code
+        return code
 
     def set(self, row: int, doc: Optional[dict]) -> None:
         if row >= self.codes.shape[0]:
@@ -189,13 +196,16 @@ class _ColumnIndex:
 
     def wanted_codes(self, values) -> Optional[list[int]]:
         """Codes of the filter values that occur in the column (None if the key is unsupported)."""
+        if not self.ok:
+            return None
         out = []
-        for v in values:
-            c = self._code(v, False)
-            if not self.ok:
-                return None
-            if c >= 0:
-                out.append(c)
+        try:
+            for v in values:
+                c = self._code(v, False)
+                if c >= 0:
+                    out.append(c)
+        except TypeError:  # unhashable filter value: unsupported for THIS query only
+            return None
         return out
 
     def sync_device(self, engine, n: int) -> None:
@@ -221,13 +231,9 @@ class _ColumnIndex:
     def match(self, values, n: int) -> Optional[np.ndarray]:
         """bool mask over rows [0, n) whose value equals one of ``values``; None if unsupported."""
         self.resize(n)
-        wanted = []
-        for v in values:
-            c = self._code(v, False)
-            if not self.ok:
-                return None
-            if c >= 0:
-                wanted.append(c)
+        wanted = self.wanted_codes(values)
+        if wanted is None:
+            return None
         codes = self.codes[:n]
         if not wanted:
             return np.zeros(n, dtype=bool)
@@ -325,13 +331,16 @@ class PicoVectorDB:
         if device is None:
             device = int(os.getenv("PICOVDB_DEVICE", "0"))
         self._device = device
+        # the reference ignores capacity= when it loads existing files (pico_vdb.py:227-284): only a
+        # fresh DB is pinned to its pre-allocation
+        loading = os.path.exists(_ids_path(storage_file)) and os.path.exists(_vecs_path(storage_file))
         self._engine = type(self)._engine_factory(
             self.dim,
             device=device,
             reserve_rows=int(capacity) if capacity else 0,
             keep_f32=keep_f32,
             bf16_mirror=bf16_mirror,
-            fixed_capacity=capacity is not None,
+            fixed_capacity=capacity is not None and not loading,
         )
         self._host_cache: Optional[np.ndarray] = None  # lazily downloaded copy behind `_vectors`
         self._columns: dict[str, _ColumnIndex] = {}    # metadata key -> columnar index (lazy)
@@ -344,10 +353,19 @@ class PicoVectorDB:
         """Host copy of the device matrix, (rows, dim) C-contiguous fp32 (downloaded on demand)."""
         if self._host_cache is None:
             n = len(self._ids)
-            self._host_cache = (
-                self._engine.download(0, n) if n else np.empty((0, self.dim), dtype=Float)
-            )
+            self._host_cache = self._download(0, n) if n else np.empty((0, self.dim), dtype=Float)
         return self._host_cache
+
+    def _download(self, row0: int, n: int) -> np.ndarray:
+        """Rows [row0, row0 + n) as fp32; slots the engine has never written (a fresh ``capacity=``
+        DB, pico_vdb.py:286-296) read as zeros, as in the reference's pre-allocated matrix."""
+        have = max(0, min(n, int(self._engine.rows) - row0))
+        if have == n:
+            return self._engine.download(row0, n)
+        out = np.zeros((n, self.dim), dtype=Float)
+        if have:
+            out[:have] = self._engine.download(row0, have)
+        return out
 
     def _invalidate(self) -> None:
         self._host_cache = None
@@ -479,7 +497,7 @@ class PicoVectorDB:
         step = max(1, (64 << 20) // (self.dim * 4))
         for r0 in range(lo, hi, step):
             r1 = min(hi, r0 + step)
-            out[r0:r1] = eng.download(r0, r1 - r0)
+            out[r0:r1] = self._download(r0, r1 - r0)
         out.flush()
         del out
         self._engine_barrier()

@@ -174,12 +174,14 @@ class DeviceStore:
         normalized: bool = False,
         rescore: bool = True,
         scan_only: bool = False,
+        guard: bool = True,
     ) -> tuple[np.ndarray, np.ndarray]:
         """(Q, dim) fp32 queries -> (scores (Q, k) f32 descending, rows (Q, k) int64).
 
         ``prefilter`` is a bool row mask or already-packed uint32 words; rows must have both
         their active bit and their prefilter bit set to be scored.  Short results are padded with
-        -inf / -1.
+        -inf / -1.  ``guard=False`` skips the exactness guard of the tensor-core precisions (see
+        ``pvdb_store_guard_stats`` in the header).
         """
         q = _f32c(queries)
         if q.ndim != 2 or q.shape[1] != self.dim:
@@ -199,14 +201,21 @@ class DeviceStore:
             flags |= N.SEARCH_NO_RESCORE
         if scan_only:
             flags |= N.SEARCH_SCAN_ONLY
+        if not guard:
+            flags |= N.SEARCH_NO_GUARD
         scores = np.empty((nq, k), dtype=np.float32)
         rows = np.empty((nq, k), dtype=np.int64)
         N.check(self._lib.pvdb_search(self.handle, _ptr(q), nq, k, _ptr(bits), flags, _ptr(scores), _ptr(rows)))
         return scores, rows
 
-    # -- metadata columns (on-device dict `where` filters) ---------------------------------------
-    MAX_COLUMNS = 16
+    def guard_stats(self) -> tuple[int, int]:
+        """(queries of the last search, of all searches) that the tensor-core path could not prove
+        exact and answered again with the exact scan."""
+        last, total = C.c_int64(0), C.c_int64(0)
+        N.check(self._lib.pvdb_store_guard_stats(self.handle, C.byref(last), C.byref(total)))
+        return int(last.value), int(total.value)
 
+    # -- metadata columns (on-device dict `where` filters) ---------------------------------------
     MAX_COLUMNS = 16  # pvdb_store::kMaxColumns
     applies_row_base = True  # result rows already include set_row_base()'s offset
 
@@ -238,7 +247,7 @@ class DeviceStore:
 
     def search_dev(self, d_queries: int, nq: int, k: int, d_scores: int, d_rows: int, d_prefilter: int = 0,
                    precision: str = "auto", normalized: bool = False, rescore: bool = True, stream: int = 0,
-                   scan_only: bool = False) -> None:
+                   scan_only: bool = False, guard: bool = True) -> None:
         """Device pointers in / out; only enqueues work on ``stream`` (a ``cudaStream_t`` as int;
         0 = CUDA's legacy default stream, which is also torch's default stream)."""
         flags = N.PRECISIONS[precision]
@@ -248,6 +257,8 @@ class DeviceStore:
             flags |= N.SEARCH_NO_RESCORE
         if scan_only:
             flags |= N.SEARCH_SCAN_ONLY
+        if not guard:
+            flags |= N.SEARCH_NO_GUARD
         N.check(
             self._lib.pvdb_search_dev(
                 self.handle, C.c_void_p(d_queries), int(nq), int(k), C.c_void_p(d_prefilter or None), flags,

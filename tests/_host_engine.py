@@ -86,7 +86,7 @@ class HostEngine:
         return self.active.copy()
 
     def search(self, queries, k, prefilter: Optional[np.ndarray] = None, precision="auto", normalized=False,
-               rescore=True):
+               rescore=True, scan_only=False, guard=True):
         self.calls.append("search")
         qn = np.ascontiguousarray(queries, np.float32) if normalized else O.prepare_queries(queries, self.dim)[0]
         pf = None

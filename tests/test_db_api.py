@@ -364,6 +364,32 @@ def test_capacity_preallocation(make_db, tmp_path):
     assert ids_of(db.query(np.array([1.0, 1.0], np.float32), top_k=1)) in (["1"], ["2"], ["3"], ["4"])
 
 
+def test_fresh_capacity_db_reads_and_saves_zero_rows(make_db, tmp_path):
+    # reference pico_vdb.py:286-296: a fresh capacity= DB is an all-zero matrix that can be read
+    # (get_all(include_vector=True), _vectors) and saved before anything was upserted
+    db = make_db(dim=4, name="capz", capacity=6)
+    assert db._vectors.shape == (6, 4) and not db._vectors.any()
+    db.save()
+    assert np.load(str(tmp_path / "capz.vecs.npy")).shape == (6, 4)
+    db.upsert([{K_ID: "a", K_VECTOR: [0, 2, 0, 0]}])
+    assert db._vectors.shape == (6, 4) and np.count_nonzero(db._vectors) == 1
+    recs = db.get_all(include_vector=True)
+    assert ids_of(recs) == ["a"]
+    db.save()
+    mat = np.load(str(tmp_path / "capz.vecs.npy"))
+    assert mat.shape == (6, 4) and np.count_nonzero(mat) == 1
+
+
+def test_capacity_is_ignored_when_loading_a_larger_store(make_db, tmp_path):
+    # reference pico_vdb.py:227-284: load takes the stored row count, whatever capacity= says
+    db = make_db(dim=3, name="grow")
+    db.upsert([{K_ID: str(i), K_VECTOR: np.eye(3, dtype=np.float32)[i % 3] + i} for i in range(7)])
+    db.save()
+    again = make_db(dim=3, name="grow", capacity=4)
+    assert again.count() == 7
+    assert ids_of(again.query(np.eye(3, dtype=np.float32)[0], top_k=1)) == ["0"]
+
+
 # ------------------------------------------------------------------ getters / counters
 def test_getters_and_counters(make_db):
     # reference tests/test_task6_getters_include_vector.py, test_task7, test_task8, test_task32

@@ -446,3 +446,75 @@ def test_batch_duplicate_rows_tie_order(store_factory, precision, mirror):
     sc3 = sc.reshape(nq, k // 3, 3)
     assert (sc3.max(axis=2) == sc3.min(axis=2)).all()              # and with identical scores
     assert rows[:5, 0].tolist() == [0, 1, 2, 3, 4]
+
+
+# ------------------------------------------------------------------ exactness guard of the tensor paths
+def _near_duplicate_corpus(n, dim, n_dup, scale, seed):
+    """Gaussian rows plus `n_dup` near-copies of one vector: base + scale * noise, normalised."""
+    rng = np.random.default_rng(seed)
+    rows = rng.standard_normal((n, dim)).astype(np.float32)
+    base = rng.standard_normal(dim).astype(np.float32)
+    base /= np.linalg.norm(base)
+    where = rng.choice(n, n_dup, replace=False)
+    noise = rng.standard_normal((n_dup, dim)).astype(np.float32) / np.sqrt(dim)
+    rows[where] = base[None, :] + np.float32(scale) * noise
+    queries = base[None, :] + 0.7 * rng.standard_normal((12, dim)).astype(np.float32) / np.sqrt(dim)
+    return rows, queries.astype(np.float32), where
+
+
+@pytest.mark.parametrize("prec,mirror", [("tf32", False), ("bf16", True)])
+def test_guard_near_duplicates_fall_back_to_exact_scan(store_factory, prec, mirror):
+    """500 near-duplicates whose mutual score differences (~1e-3 * noise) sit far below the tensor
+    core's input rounding error: ranking them by tf32 / bf16 scores is a lottery, so top-10 + 32 (54)
+    candidates miss true top-10 rows.  The guard must notice (the re-scored 10th best is not provably
+    above the weakest kept candidate + rounding bound) and re-run those queries on the exact scan:
+    ids then equal the fp32 scan's / the oracle's.  Without the guard the same call is wrong."""
+    dim, n, k = 128, 20_000, 10
+    raw, queries, _ = _near_duplicate_corpus(n, dim, 500, 1e-3, 7)
+    s = store_factory(dim, bf16_mirror=mirror)
+    s.upsert_range(raw, 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(queries, dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    exact_s, exact_r = s.search(queries, k, precision="f32")          # one exact scan per query
+    O.compare_topk(exact_s, exact_r, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+
+    got_s, got_r = s.search(queries, k, precision=prec)               # guarded tensor-core batch
+    flagged, _ = s.guard_stats()
+    assert flagged == len(queries), f"every query sits in the near-duplicate cluster, {flagged} flagged"
+    np.testing.assert_array_equal(got_r, exact_r)
+    np.testing.assert_array_equal(got_s, exact_s)
+
+    raw_s, raw_r = s.search(queries, k, precision=prec, guard=False)  # what round 1 returned
+    assert s.guard_stats()[0] == 0
+    assert O.recall_at_k(raw_r, exact_r) < 0.9, "the corpus must actually defeat the fixed slack"
+
+
+def test_guard_quiet_on_well_separated_data_and_batch_equals_single(store_factory):
+    """Gaussian data: nothing is flagged, and a query returns the same ids alone (exact scan) and
+    inside a batch (tensor-core pass + re-scoring), on an fp32 store and on a bf16-only store."""
+    dim, n, k, nq = 384, 30_000, 10, 150
+    raw = _gauss(n, dim, 81)
+    queries = _gauss(nq, dim, 82)
+    for kw, prec in (({}, "tf32"), ({"keep_f32": False, "bf16_mirror": True}, "bf16")):
+        s = store_factory(dim, **kw)
+        s.upsert_range(raw, 0)
+        b_s, b_r = s.search(queries, k, precision=prec)
+        assert s.guard_stats()[0] == 0
+        for qi in range(0, nq, 7):
+            o_s, o_r = s.search(queries[qi:qi + 1], k)                # single query: exact scan of this store
+            np.testing.assert_array_equal(b_r[qi], o_r[0])
+            np.testing.assert_allclose(b_s[qi], o_s[0], rtol=2e-6, atol=1e-6)
+
+
+def test_guard_large_k_slack(store_factory):
+    """k = 100 takes the wider slack (k_sel = 160): still exact, nothing flagged on Gaussian rows."""
+    dim, n, k, nq = 768, 40_000, 100, 64
+    s = store_factory(dim)
+    s.upsert_range(_gauss(n, dim, 91), 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 92), dim)
+    ref_s, ref_r = O.search(store, qn, k)
+    sc, rows = s.search(qn, k, precision="tf32", normalized=True)
+    assert s.guard_stats()[0] == 0
+    O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)

@@ -104,6 +104,22 @@ def test_unhashable_values_fall_back_to_the_loop(make_db):
     assert not db._columns["tags"].ok
 
 
+def test_unhashable_filter_value_does_not_disable_the_column(make_db):
+    # an unhashable FILTER value says nothing about the stored data: that one query takes the Python
+    # loop, the column index (and its device mirror) stays usable for the next one
+    db = make_db()
+    db.upsert([
+        {K_VECTOR: [1, 0, 0, 0], K_ID: "a", "tag": "x"},
+        {K_VECTOR: [0, 1, 0, 0], K_ID: "b", "tag": "y"},
+    ])
+    q = np.array([1, 1, 0, 0], np.float32)
+    assert [r[K_ID] for r in db.query(q, where={"tag": "x"})] == ["a"]
+    assert db.query(q, where={"tag": ["x", "y"]}) == [[]]          # no stored value equals the list
+    assert db.query(q, where={"tag": {"nested": 1}}) == [[]]
+    assert db._columns["tag"].ok
+    assert [r[K_ID] for r in db.query(q, where={"tag": "y"})] == ["b"]
+
+
 def _ids_of(res):
     if res and isinstance(res[0], list):   # no candidates: the reference returns [[]] even for one query
         return [[r[K_ID] for r in lst] for lst in res]
