@@ -595,8 +595,11 @@ def run_b200(args, world, rank, local_rank):
         assert N.kernel_launches() - l0 == n_scan, "roofline loop must launch exactly one kernel per query"
         scan_ms = ev0.elapsed_time(ev1) / n_scan
 
-        dev_ms, e2e_ms, scan_ms, b_ms, b_e2e_ms, fill_s = max_over_ranks(
-            [dev_ms, e2e_s * 1e3, scan_ms, b_ms or 0.0, b_e2e_ms or 0.0, fill_s])
+        guard_last, guard_total = store.guard_stats()
+        dev_ms, e2e_ms, scan_ms, b_ms, b_e2e_ms, fill_s, guard_total = max_over_ranks(
+            [dev_ms, e2e_s * 1e3, scan_ms, b_ms or 0.0, b_e2e_ms or 0.0, fill_s, float(guard_total)])
+        exchange_mode = sharded.exchange_mode
+        sharded.close()
         store.close()
         del sharded, store
         torch.cuda.empty_cache()
@@ -632,6 +635,7 @@ def run_b200(args, world, rank, local_rank):
             "clocks": clocks,
             "parity": parity,
             "fill_seconds": fill_s,
+            "exchange": exchange_mode,
         }
         if with_batch:
             flops = 2.0 * nb * wl.rows * wl.dim
@@ -639,6 +643,7 @@ def run_b200(args, world, rank, local_rank):
             kind = "bf16" if wl.store_dtype == "bf16" else "tf32 (peak taken as bf16 / 2)"
             scale = 1.0 if wl.store_dtype == "bf16" else 0.5
             batch_out.update({
+                "guard_flagged_queries": int(guard_total),   # fell back to the exact scan (all batch calls of this run)
                 "queries": nb,
                 "k": k,
                 "ms_per_batch": b_ms,
@@ -712,6 +717,7 @@ def run_b200(args, world, rank, local_rank):
             "parity": main["parity"],
             "fill_seconds": main["fill_seconds"],
         }
+        line["exchange_mode"] = main["exchange"]   # mechanism actually used (config stays identical to the reference arm's)
         if "batch" in main:
             line["batch"] = main["batch"]
         if c2 is not None:

@@ -57,6 +57,9 @@ extern "C" {
 #define PVDB_SEARCH_NO_GUARD 0x800           /* tensor-core paths: skip the exactness guard (see pvdb_search) */
 
 typedef struct pvdb_store pvdb_store_t;
+typedef struct pvdb_exchange pvdb_exchange_t; /* one GPU's end of the cross-GPU top-k exchange */
+typedef struct pvdb_group pvdb_group_t;       /* a row-sharded store over several GPUs of one process */
+#define PVDB_IPC_HANDLE_BYTES 64
 
 typedef struct pvdb_store_info {
   int32_t dim;          /* embedding dimension */
@@ -155,6 +158,56 @@ int pvdb_store_guard_stats(pvdb_store_t* s, int64_t* out_last, int64_t* out_tota
 int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
                     const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
                     int64_t* d_out_rows, void* stream);
+
+/* ---- multi-GPU: row shards + peer-memory exchange (no reference counterpart) ---
+ * The database rows are split into contiguous shards, one pvdb_store_t per GPU with row_base = the
+ * shard's first global row.  Every GPU answers a query from its shard; the per-GPU top-k lists are
+ * then exchanged and merged.  The exchange does not go through a collective library: every GPU owns
+ * a mailbox in its HBM that all peers can write over NVLink (CUDA IPC between processes, peer access
+ * inside one process), and the kernel that finishes a local list stores it into every peer's
+ * mailbox, raises a flag, waits for the peers' flags and merges -- inside the scan kernel for single
+ * queries, in one extra kernel after a tensor-core batch.  Every GPU ends with the same final top k.
+ *
+ * One exchange end per GPU, one GPU per process-or-thread: kernels that wait for each other must not
+ * share a GPU.  All ranks must make the same pvdb_search_exchange* calls in the same order.
+ * slot_keys = the largest nq * k one call may produce; k <= 128 (larger k: gather the per-shard
+ * results and use pvdb_merge_topk_dev).  The wait is bounded (~4 s), then the kernel traps. */
+int pvdb_exchange_create(pvdb_exchange_t** out, int device, int world, int rank, int64_t slot_keys);
+int pvdb_exchange_destroy(pvdb_exchange_t* ex);
+/* Between processes: export this end's mailbox (PVDB_IPC_HANDLE_BYTES bytes), all-gather the handles
+ * by any means, then connect with the `world` handles in rank order. */
+int pvdb_exchange_ipc_handle(pvdb_exchange_t* ex, void* out_handle);
+int pvdb_exchange_connect_ipc(pvdb_exchange_t* ex, const void* handles);
+/* Unmap the peers' mailboxes.  Tear-down order between processes: every rank disconnects, a barrier,
+ * then every rank destroys (a mailbox must not be freed while a peer still maps it). */
+int pvdb_exchange_disconnect(pvdb_exchange_t* ex);
+/* Inside one process: connect the `world` ends exs[0..world) (distinct devices, peer access). */
+int pvdb_exchange_connect_local(pvdb_exchange_t** exs, int world);
+int pvdb_exchange_info(pvdb_exchange_t* ex, int* out_world, int* out_rank, int64_t* out_slot_keys,
+                       int64_t* out_launches);
+/* pvdb_search / pvdb_search_dev on one shard with the exchange fused in: the outputs are the merged
+ * top k over all shards (global rows). */
+int pvdb_search_exchange(pvdb_store_t* s, pvdb_exchange_t* ex, const float* queries, int64_t nq, int k,
+                         const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows);
+int pvdb_search_exchange_dev(pvdb_store_t* s, pvdb_exchange_t* ex, const float* d_queries, int64_t nq,
+                             int k, const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
+                             int64_t* d_out_rows, void* stream);
+
+/* Single-process form (the `devices=[...]` keyword of the Python class): one handle that owns a
+ * shard store + exchange end per listed device (distinct devices, peer access required) and a worker
+ * thread per device.  Global row r lives in shard r / rows_per_shard (contiguous blocks of
+ * ceil(capacity_rows / ndev) rows rounded up to 32).  Writes go through the per-shard store handles
+ * (pvdb_group_store; rows local to the shard = global row - shard * rows_per_shard); a search is ONE
+ * call: every shard scans its rows, the lists are exchanged over NVLink inside the kernels, shard 0's
+ * copy of the merged result is returned.  prefilter_bits is the GLOBAL bitmap (ceil(capacity/32)
+ * words).  slot_keys <= 0 selects 65536 (nq * k of one call must fit). */
+int pvdb_group_create(pvdb_group_t** out, const int* devices, int ndev, int dim, int64_t capacity_rows,
+                      int flags, int64_t slot_keys);
+int pvdb_group_destroy(pvdb_group_t* g);
+int pvdb_group_size(pvdb_group_t* g, int* out_world, int64_t* out_rows_per_shard);
+pvdb_store_t* pvdb_group_store(pvdb_group_t* g, int shard);
+int pvdb_group_search(pvdb_group_t* g, const float* queries, int64_t nq, int k,
+                      const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows);
 
 /* k-way merge of nlists per-shard results (what an all-gather of the per-GPU outputs produces)
  * into [nq][k]; rows are global already.  List l's scores start at d_scores + l*scores_stride

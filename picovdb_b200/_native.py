@@ -28,6 +28,7 @@ SEARCH_QUERIES_NORMALIZED = 0x100
 SEARCH_NO_RESCORE = 0x200
 SEARCH_SCAN_ONLY = 0x400
 SEARCH_NO_GUARD = 0x800
+IPC_HANDLE_BYTES = 64
 
 PRECISIONS = {"auto": PREC_AUTO, "f32": PREC_F32, "fp32": PREC_F32, "tf32": PREC_TF32, "bf16": PREC_BF16}
 
@@ -87,6 +88,20 @@ SIGNATURES = {
     "pvdb_store_column_drop": (C.c_int, [_P, C.c_int]),
     "pvdb_search_dev": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P, _P]),
     "pvdb_store_guard_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I64)]),
+    "pvdb_exchange_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _I64]),
+    "pvdb_exchange_destroy": (C.c_int, [_P]),
+    "pvdb_exchange_ipc_handle": (C.c_int, [_P, _P]),
+    "pvdb_exchange_connect_ipc": (C.c_int, [_P, _P]),
+    "pvdb_exchange_disconnect": (C.c_int, [_P]),
+    "pvdb_exchange_connect_local": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "pvdb_exchange_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_I64), C.POINTER(_I64)]),
+    "pvdb_search_exchange": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P, C.c_int, _P, _P]),
+    "pvdb_search_exchange_dev": (C.c_int, [_P, _P, _P, _I64, C.c_int, _P, C.c_int, _P, _P, _P]),
+    "pvdb_group_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_int, _I64, C.c_int, _I64]),
+    "pvdb_group_destroy": (C.c_int, [_P]),
+    "pvdb_group_size": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(_I64)]),
+    "pvdb_group_store": (_P, [_P, C.c_int]),
+    "pvdb_group_search": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P]),
     "pvdb_merge_topk_dev": (C.c_int, [C.c_int, _P, _P, C.c_int, _I64, C.c_int, _I64, _I64, _P, _P, _P]),
     "pvdb_kernel_launches": (_I64, []),
 }

@@ -1,8 +1,10 @@
 // C ABI: search + merge entry points (the read side of the hot path).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "batch.cuh"
+#include "exchange.cuh"
 #include "scan.cuh"
 #include "store.cuh"
 
@@ -31,8 +33,11 @@ static int fill_empty(float* d_scores, int64_t* d_rows, int64_t n, cudaStream_t 
 // kernel keeps on the device, so no host round trip separates the passes.
 // d_qn: normalised queries (nq x ldq) or NULL, in which case d_raw (nq x dim, raw) is normalised by
 // the scan kernel itself.
+// ex (optional, k <= kFusedK only): every launch exchanges its list with the peer GPUs inside the
+// kernel and writes the merged, final top k (one exchange sequence number per query).
 static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float* d_raw, int64_t nq, int k,
-                       const uint32_t* d_pref, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+                       const uint32_t* d_pref, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st,
+                       pvdb_exchange* ex = nullptr) {
   const int grid = scan_grid_blocks();
   const size_t list_bytes = static_cast<size_t>(grid) * kFusedK * sizeof(uint64_t);
   PVDB_TRY(s->d_partial.ensure(list_bytes + 64));
@@ -61,6 +66,8 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
       p.upper = (k0 == 0) ? nullptr : p.next_upper;
       p.out_scores = d_out_scores + q * k + k0;
       p.out_rows = d_out_rows + q * k + k0;
+      p.xv = ExchangeView{};
+      if (ex != nullptr) p.xv = ex->next_view();
       PVDB_TRY(launch_scan(p, bf16, st));
     }
   }
@@ -68,9 +75,22 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
 }
 
 // Device-side search shared by both entry points.  d_queries is nq x dim fp32 (raw).
+// ex (optional): this store is one shard of a row-sharded database; the results written are the
+// MERGED top k over all shards (every rank makes the same call and ends with the same answer).
 static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int k, const uint32_t* d_pref,
-                         int flags, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st) {
+                         int flags, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st,
+                         pvdb_exchange* ex = nullptr) {
   if (nq == 0) return PVDB_OK;
+  // a world of one has nobody to exchange with; PVDB_EXCHANGE_SELF=1 keeps the (self-)mailbox steps
+  // in the kernels anyway so that a single-GPU box can test them
+  if (ex != nullptr && ex->world <= 1 && getenv("PVDB_EXCHANGE_SELF") == nullptr) ex = nullptr;
+  if (ex != nullptr) {
+    if (!ex->connected) return fail(PVDB_ERR_INVALID, "search: the exchange is not connected to its peers");
+    if (k > kFusedK) return fail(PVDB_ERR_UNSUPPORTED, "search: the fused exchange serves k <= %d", kFusedK);
+    if (nq * k > ex->slot_keys)
+      return fail(PVDB_ERR_INVALID, "search: %lld x %d results exceed the exchange slot (%lld keys)", (long long)nq, k,
+                  (long long)ex->slot_keys);
+  }
   int prec = flags & PVDB_PREC_MASK;
   const bool has_f32 = (s->flags & PVDB_STORE_F32) != 0;
   const bool has_b16 = (s->flags & PVDB_STORE_BF16) != 0;
@@ -84,7 +104,7 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
     return fail(PVDB_ERR_UNSUPPORTED, "search: this store keeps no fp32 matrix");
   if (prec == PVDB_PREC_BF16 && !has_b16) return fail(PVDB_ERR_UNSUPPORTED, "search: this store keeps no bf16 mirror");
   if (prec < PVDB_PREC_F32 || prec > PVDB_PREC_BF16) return fail(PVDB_ERR_INVALID, "search: unknown precision %d", prec);
-  if (s->rows == 0) return fill_empty(d_out_scores, d_out_rows, nq * k, st);
+  if (s->rows == 0 && ex == nullptr) return fill_empty(d_out_scores, d_out_rows, nq * k, st);
 
   const bool want_rescore = !(flags & PVDB_SEARCH_NO_RESCORE);
   const bool batch = batch_path_available() && nq >= kBatchMinQueries && !(flags & PVDB_SEARCH_SCAN_ONLY) &&
@@ -96,6 +116,25 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
   // the raw low-precision scores
   const bool guard = batch && want_rescore && !(flags & PVDB_SEARCH_NO_GUARD);
   s->guard_flagged_last = 0;
+  // With an exchange, the batch path (and an empty shard) first produce this shard's lists in
+  // scratch; one exchange + merge launch then writes the final result.  The scan path exchanges
+  // inside the scan kernel itself.  Every rank takes the same path (it depends on the arguments and
+  // the store layout only), so all ranks consume the same exchange sequence numbers.
+  float* d_fin_scores = d_out_scores;
+  int64_t* d_fin_rows = d_out_rows;
+  if (ex != nullptr && (batch || s->rows == 0)) {
+    PVDB_TRY(s->d_xloc.ensure(static_cast<size_t>(nq) * k * (sizeof(int64_t) + sizeof(float))));
+    d_out_rows = static_cast<int64_t*>(s->d_xloc.ptr);
+    d_out_scores = reinterpret_cast<float*>(d_out_rows + nq * k);
+  }
+  if (s->rows == 0) {  // only reached with an exchange: publish empty lists, collect the peers'
+    PVDB_TRY(fill_empty(d_out_scores, d_out_rows, nq * k, st));
+    if (batch) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
+    for (int64_t q = 0; q < nq; ++q)
+      PVDB_TRY(launch_exchange_merge(ex, d_out_scores + q * k, d_out_rows + q * k, 1, k, d_fin_scores + q * k,
+                                     d_fin_rows + q * k, st));
+    return PVDB_OK;
+  }
   const float* d_qn = nullptr;
   __nv_bfloat16* d_qn16 = nullptr;
   float* d_qeps = nullptr;
@@ -140,7 +179,10 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
     }
     PVDB_TRY(search_batch(s, prec == PVDB_PREC_BF16, d_qn, d_qn16, nq, k, d_pref, !want_rescore, d_qeps, d_flag_count,
                           d_flag_list, d_out_scores, d_out_rows, st));
-    if (!guard) return PVDB_OK;
+    if (!guard) {
+      if (ex != nullptr) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
+      return PVDB_OK;
+    }
     // The one host round trip of a guarded tensor-core search: how many queries could not be PROVEN
     // exact?  (Normally none; near-duplicate corpora flag many.)  Those are answered again by the
     // exact scan of the same store -- fp32 rows when the store has them, else the bf16 rows -- which
@@ -151,9 +193,9 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
     const int64_t n_flag = std::min<int64_t>(static_cast<unsigned>(h[0]), nq);
     s->guard_flagged_last = n_flag;
     s->guard_flagged_total += n_flag;
-    if (n_flag == 0) return PVDB_OK;
+    if (n_flag > 0)
     PVDB_CUDA(cudaMemcpyAsync(h + 4, d_flag_list, static_cast<size_t>(n_flag) * sizeof(int), cudaMemcpyDeviceToHost, st));
-    PVDB_CUDA(cudaStreamSynchronize(st));
+    if (n_flag > 0) PVDB_CUDA(cudaStreamSynchronize(st));
     for (int64_t i = 0; i < n_flag; ++i) {
       const int64_t q = h[4 + i];
       if (q < 0 || q >= nq) return fail(PVDB_ERR_CUDA, "guard: corrupt flag list");
@@ -165,10 +207,11 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
         PVDB_TRY(search_scan(s, !has_f32, nullptr, d_queries + q * s->dim, 1, k, d_pref, d_out_scores + q * k,
                              d_out_rows + q * k, st));
     }
+    if (ex != nullptr) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
     return PVDB_OK;
   }
   // scan path: TF32 requests with few queries are served by the exact fp32 scan
-  return search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st);
+  return search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st, ex);
 }
 
 }  // namespace pvdb
@@ -178,20 +221,35 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
   std::lock_guard<std::mutex> _guard((s)->mu);                            \
   PVDB_CUDA(cudaSetDevice((s)->device))
 
-extern "C" int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
-                               const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
-                               int64_t* d_out_rows, void* stream) {
+static int search_dev_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* d_queries, int64_t nq, int k,
+                            const uint32_t* d_prefilter_bits, int flags, float* d_out_scores, int64_t* d_out_rows,
+                            void* stream) {
   PVDB_ENTER(s);
   if (nq < 0 || k < 1 || (nq > 0 && (!d_queries || !d_out_scores || !d_out_rows)))
     return fail(PVDB_ERR_INVALID, "search_dev: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
+  if (ex != nullptr && ex->device != s->device) return fail(PVDB_ERR_INVALID, "search: exchange and store live on different devices");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PVDB_TRY(s->use_stream(st));
-  return search_device(s, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, st);
+  return search_device(s, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, st, ex);
 }
 
-extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,
-                           const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
+extern "C" int pvdb_search_dev(pvdb_store_t* s, const float* d_queries, int64_t nq, int k,
+                               const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
+                               int64_t* d_out_rows, void* stream) {
+  return search_dev_entry(s, nullptr, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, stream);
+}
+
+extern "C" int pvdb_search_exchange_dev(pvdb_store_t* s, pvdb_exchange_t* ex, const float* d_queries, int64_t nq,
+                                        int k, const uint32_t* d_prefilter_bits, int flags, float* d_out_scores,
+                                        int64_t* d_out_rows, void* stream) {
+  if (!ex) return fail(PVDB_ERR_INVALID, "null exchange handle");
+  return search_dev_entry(s, ex, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, stream);
+}
+
+static int search_host_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* queries, int64_t nq, int k,
+                             const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
   PVDB_ENTER(s);
+  if (ex != nullptr && ex->device != s->device) return fail(PVDB_ERR_INVALID, "search: exchange and store live on different devices");
   if (nq < 0 || k < 1 || (nq > 0 && (!queries || !out_scores || !out_rows)))
     return fail(PVDB_ERR_INVALID, "search: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
   if (nq == 0) return PVDB_OK;
@@ -218,13 +276,24 @@ extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, in
   const bool zero_copy = out_bytes <= (64u << 10);
   int64_t* d_rows = static_cast<int64_t*>(zero_copy ? s->h_pinned.ptr : s->d_out.ptr);
   float* d_scores = reinterpret_cast<float*>(d_rows + n_out);
-  PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_pref, flags, d_scores, d_rows, st));
+  PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_pref, flags, d_scores, d_rows, st, ex));
   if (!zero_copy) PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
   PVDB_CUDA(cudaStreamSynchronize(st));
   const int64_t* h_rows = static_cast<const int64_t*>(s->h_pinned.ptr);
   std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
   std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
   return PVDB_OK;
+}
+
+extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,
+                           const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
+  return search_host_entry(s, nullptr, queries, nq, k, prefilter_bits, flags, out_scores, out_rows);
+}
+
+extern "C" int pvdb_search_exchange(pvdb_store_t* s, pvdb_exchange_t* ex, const float* queries, int64_t nq, int k,
+                                    const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
+  if (!ex) return fail(PVDB_ERR_INVALID, "null exchange handle");
+  return search_host_entry(s, ex, queries, nq, k, prefilter_bits, flags, out_scores, out_rows);
 }
 
 extern "C" int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t nq, int k, int column,

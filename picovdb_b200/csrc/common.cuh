@@ -162,6 +162,46 @@ struct WarpList {
   }
 };
 
+// ---------------------------------------------------------------------------- list merging
+template <bool GLOBAL>
+__device__ __forceinline__ uint64_t load_key(const uint64_t* p) {
+  if constexpr (GLOBAL) {
+    return __ldcg(reinterpret_cast<const unsigned long long*>(p));  // L2: written by other SMs
+  } else {
+    return *p;
+  }
+}
+
+template <bool GLOBAL, int S>
+__device__ __forceinline__ void merge_list(WarpList<S>& L, uint64_t& thr, const uint64_t* src, int n, int k,
+                                           int lane) {
+  // src: descending list of n keys; k: rank whose key is the admission threshold
+  for (int base = 0; base < n; base += 32) {
+    const int e = base + lane;
+    const uint64_t v = (e < n) ? load_key<GLOBAL>(src + e) : 0ull;
+    unsigned m = __ballot_sync(0xffffffffu, v > thr);
+    if (m == 0) break;  // lists are descending: nothing further can qualify
+    while (m) {
+      const int srcl = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t x = shfl_u64(v, srcl);
+      if (x > thr) {
+        L.insert(x, lane);
+        thr = L.get(k - 1);
+      }
+    }
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void store_list(const WarpList<S>& L, uint64_t* dst, int k, int lane) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int e = s * 32 + lane;
+    if (e < k) dst[e] = L.slot[s];
+  }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace pvdb

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "exchange.cuh"
 
 namespace pvdb {
 
@@ -35,6 +36,8 @@ struct ScanParams {
   float* out_scores;         // [k]
   int64_t* out_rows;         // [k]
   int64_t row_base;
+  ExchangeView xv;           // xv.world > 0: the last block exchanges its list with the peer GPUs and
+                             // merges theirs before writing the result (exchange.cuh); not with paging
 };
 
 // Launch one scan pass on `stream`.  `is_bf16` selects the mirror layout.

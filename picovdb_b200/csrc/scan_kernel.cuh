@@ -10,45 +10,6 @@ namespace pvdb {
 
 
 
-template <bool GLOBAL>
-__device__ __forceinline__ uint64_t load_key(const uint64_t* p) {
-  if constexpr (GLOBAL) {
-    return __ldcg(reinterpret_cast<const unsigned long long*>(p));  // L2: written by other SMs
-  } else {
-    return *p;
-  }
-}
-
-template <bool GLOBAL, int S>
-__device__ __forceinline__ void merge_list(WarpList<S>& L, uint64_t& thr, const uint64_t* src, int n, int k,
-                                           int lane) {
-  // src: descending list of n keys; k: rank whose key is the admission threshold
-  for (int base = 0; base < n; base += 32) {
-    const int e = base + lane;
-    const uint64_t v = (e < n) ? load_key<GLOBAL>(src + e) : 0ull;
-    unsigned m = __ballot_sync(0xffffffffu, v > thr);
-    if (m == 0) break;  // lists are descending: nothing further can qualify
-    while (m) {
-      const int srcl = __ffs(m) - 1;
-      m &= m - 1;
-      const uint64_t x = shfl_u64(v, srcl);
-      if (x > thr) {
-        L.insert(x, lane);
-        thr = L.get(k - 1);
-      }
-    }
-  }
-}
-
-template <int S>
-__device__ __forceinline__ void store_list(const WarpList<S>& L, uint64_t* dst, int k, int lane) {
-#pragma unroll
-  for (int s = 0; s < S; ++s) {
-    const int e = s * 32 + lane;
-    if (e < k) dst[e] = L.slot[s];
-  }
-}
-
 __device__ __forceinline__ float dot_chunk_f32(const uint4& v, const float4& q, float acc) {
   acc = fmaf(__uint_as_float(v.x), q.x, acc);
   acc = fmaf(__uint_as_float(v.y), q.y, acc);
@@ -296,13 +257,38 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   __syncthreads();
   if (warp == 0) {
     for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
+    int64_t out_base = p.row_base;
+    if (p.xv.world > 0) {
+      // ---- cross-GPU exchange, fused (exchange.cuh): this GPU's list goes into every peer's
+      // mailbox as keys with global rows, the peers' lists arrive in ours, and the k-way merge of
+      // the `world` lists happens right here -- the kernel writes the FINAL top k on every GPU.
+      const ExchangeView& v = p.xv;
+      const int parity = static_cast<int>(v.seq & 1ull);
+      for (int peer = 0; peer < v.world; ++peer) {
+        uint64_t* dst = xv_slot(v, v.box[peer], parity, v.rank);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int e = s * 32 + lane;
+          if (e < k) dst[e] = key_to_global(L.slot[s], p.row_base);
+        }
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane < v.world) st_release_sys(xv_flag(v.box[lane], parity, v.rank, 0), v.seq);
+      if (lane < v.world) xv_wait_flag(xv_flag(v.box[v.rank], parity, lane, 0), v.seq);
+      __syncwarp();
+      L.clear();
+      thr = 0ull;
+      for (int r = 0; r < v.world; ++r) merge_list<true, S>(L, thr, xv_slot(v, v.box[v.rank], parity, r), k, k, lane);
+      out_base = 0;  // the merged keys carry global rows
+    }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int e = s * 32 + lane;
       if (e < k) {
         const uint64_t key = L.slot[s];
         p.out_scores[e] = key ? key_score(key) : -INFINITY;
-        p.out_rows[e] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
+        p.out_rows[e] = key ? out_base + static_cast<int64_t>(key_row(key)) : -1ll;
       }
     }
     const uint64_t kth = L.get(k - 1);

@@ -465,7 +465,7 @@ extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
   s->active.release();
   s->drop_columns();
   for (Scratch* sc : {&s->d_in, &s->d_rows, &s->d_prefilter, &s->d_qn, &s->d_qn16, &s->d_partial, &s->d_out,
-                      &s->d_misc, &s->h_pinned, &s->d_qeps, &s->d_flag, &s->h_flag})
+                      &s->d_misc, &s->h_pinned, &s->d_qeps, &s->d_flag, &s->h_flag, &s->d_xloc})
     sc->release();
   if (s->d_err_words) cudaFree(s->d_err_words);
   if (s->order_event) cudaEventDestroy(s->order_event);

@@ -81,6 +81,7 @@ struct pvdb_store {
   pvdb::Scratch h_pinned;   // pinned bounce buffer for results
   pvdb::Scratch d_qeps;     // per query: ||q - tf32(q)||, ||q - bf16(q)|| (exactness guard of the tensor paths)
   pvdb::Scratch d_flag;     // guard: [count][flagged query indices]
+  pvdb::Scratch d_xloc;     // this shard's lists before the cross-GPU exchange: [nq*k] rows, then scores
   pvdb::Scratch h_flag;     // pinned copy of d_flag
   // Largest input-rounding error over the rows ever written, as the uint image of two non-negative
   // floats: [0] = max_r ||v_r - tf32_trunc(v_r)||^2, [1] = max_r ||v_r - bf16_rn(v_r)||^2.  Only

@@ -283,6 +283,7 @@ class PicoVectorDB:
         argsort_threshold: Optional[float] = None,
         # ---- B200 engine options (no reference counterpart) ----
         device: Optional[int] = None,
+        devices: Optional[list[int]] = None,
         bf16_mirror: bool = False,
         keep_f32: bool = True,
         precision: str = "auto",
@@ -334,7 +335,21 @@ class PicoVectorDB:
         # the reference ignores capacity= when it loads existing files (pico_vdb.py:227-284): only a
         # fresh DB is pinned to its pre-allocation
         loading = os.path.exists(_ids_path(storage_file)) and os.path.exists(_vecs_path(storage_file))
-        self._engine = type(self)._engine_factory(
+        factory = type(self)._engine_factory
+        if devices is not None and len(devices) > 1:
+            # one process, several GPUs: rows sharded over `devices`, searches merged over NVLink
+            # inside the kernels (group.py); needs the total capacity to lay out the partition
+            if capacity is None:
+                raise ValueError("devices=[...] needs capacity= (the row partition over the GPUs is fixed)")
+            from .group import GroupStore
+
+            def factory(dim, **kw):  # noqa: E306
+                kw.pop("device", None)
+                return GroupStore(dim, devices, **kw)
+        elif devices:
+            device = int(devices[0])
+            self._device = device
+        self._engine = factory(
             self.dim,
             device=device,
             reserve_rows=int(capacity) if capacity else 0,

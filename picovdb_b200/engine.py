@@ -62,13 +62,25 @@ class DeviceStore:
         h = C.c_void_p()
         N.check(self._lib.pvdb_store_create(C.byref(h), int(device), int(dim), int(reserve_rows), flags))
         self._h = h
+        self._owned = True
         self.dim = int(dim)
         self.device = int(device)
+
+    @classmethod
+    def from_handle(cls, handle: C.c_void_p, dim: int, device: int) -> "DeviceStore":
+        """Non-owning view of a store that belongs to a ``pvdb_group_t`` (closing it is a no-op)."""
+        self = cls.__new__(cls)
+        self._lib = N.load()
+        self._h = handle
+        self._owned = False
+        self.dim = int(dim)
+        self.device = int(device)
+        return self
 
     # -- lifecycle ---------------------------------------------------------------------------
     def close(self) -> None:
         h, self._h = getattr(self, "_h", None), None
-        if h is not None and h.value:
+        if h is not None and h.value and getattr(self, "_owned", True):
             self._lib.pvdb_store_destroy(h)
 
     def __del__(self) -> None:  # pragma: no cover - interpreter shutdown ordering
@@ -208,6 +220,49 @@ class DeviceStore:
         N.check(self._lib.pvdb_search(self.handle, _ptr(q), nq, k, _ptr(bits), flags, _ptr(scores), _ptr(rows)))
         return scores, rows
 
+    def _search_flags(self, precision, normalized, rescore, scan_only, guard) -> int:
+        flags = N.PRECISIONS[precision]
+        if normalized:
+            flags |= N.SEARCH_QUERIES_NORMALIZED
+        if not rescore:
+            flags |= N.SEARCH_NO_RESCORE
+        if scan_only:
+            flags |= N.SEARCH_SCAN_ONLY
+        if not guard:
+            flags |= N.SEARCH_NO_GUARD
+        return flags
+
+    def search_exchange(self, ex: "Exchange", queries: np.ndarray, k: int, prefilter: Optional[np.ndarray] = None,
+                        precision: str = "auto", normalized: bool = False, rescore: bool = True,
+                        scan_only: bool = False, guard: bool = True) -> tuple[np.ndarray, np.ndarray]:
+        """``search`` on this SHARD with the cross-GPU exchange fused in: returns the merged top k over
+        all shards (global rows).  Every rank must make the same call.  ``prefilter``: this shard's rows."""
+        q = _f32c(queries)
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"search expects (Q, {self.dim}) queries")
+        nq, k = q.shape[0], int(k)
+        bits = None
+        if prefilter is not None:
+            pf = np.asarray(prefilter)
+            bits = pack_row_mask(pf) if pf.dtype == np.bool_ else np.ascontiguousarray(pf, dtype="<u4")
+        scores = np.empty((nq, k), dtype=np.float32)
+        rows = np.empty((nq, k), dtype=np.int64)
+        N.check(self._lib.pvdb_search_exchange(self.handle, ex.handle, _ptr(q), nq, k, _ptr(bits),
+                                               self._search_flags(precision, normalized, rescore, scan_only, guard),
+                                               _ptr(scores), _ptr(rows)))
+        return scores, rows
+
+    def search_exchange_dev(self, ex: "Exchange", d_queries: int, nq: int, k: int, d_scores: int, d_rows: int,
+                            d_prefilter: int = 0, precision: str = "auto", normalized: bool = False,
+                            rescore: bool = True, stream: int = 0, scan_only: bool = False, guard: bool = True) -> None:
+        N.check(
+            self._lib.pvdb_search_exchange_dev(
+                self.handle, ex.handle, C.c_void_p(d_queries), int(nq), int(k), C.c_void_p(d_prefilter or None),
+                self._search_flags(precision, normalized, rescore, scan_only, guard),
+                C.c_void_p(d_scores), C.c_void_p(d_rows), C.c_void_p(stream or None),
+            )
+        )
+
     def guard_stats(self) -> tuple[int, int]:
         """(queries of the last search, of all searches) that the tensor-core path could not prove
         exact and answered again with the exact scan."""
@@ -265,6 +320,53 @@ class DeviceStore:
                 C.c_void_p(d_scores), C.c_void_p(d_rows), C.c_void_p(stream or None),
             )
         )
+
+
+class Exchange:
+    """One GPU's end of the peer-memory top-k exchange (``pvdb_exchange_t``, include/picovdb_b200.h)."""
+
+    def __init__(self, device: int, world: int, rank: int, slot_keys: int) -> None:
+        self._lib = N.load()
+        h = C.c_void_p()
+        N.check(self._lib.pvdb_exchange_create(C.byref(h), int(device), int(world), int(rank), int(slot_keys)))
+        self._h = h
+        self.world, self.rank, self.slot_keys = int(world), int(rank), int(slot_keys)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if self._h is None:
+            raise RuntimeError("Exchange is closed")
+        return self._h
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(N.IPC_HANDLE_BYTES)
+        N.check(self._lib.pvdb_exchange_ipc_handle(self.handle, buf))
+        return buf.raw
+
+    def connect_ipc(self, handles: bytes) -> None:
+        """``handles``: the ``world`` IPC handles concatenated in rank order."""
+        if len(handles) != self.world * N.IPC_HANDLE_BYTES:
+            raise ValueError("expected one IPC handle per rank")
+        N.check(self._lib.pvdb_exchange_connect_ipc(self.handle, C.c_char_p(handles)))
+
+    def disconnect(self) -> None:
+        N.check(self._lib.pvdb_exchange_disconnect(self.handle))
+
+    def launches(self) -> int:
+        n = C.c_int64(0)
+        N.check(self._lib.pvdb_exchange_info(self.handle, None, None, None, C.byref(n)))
+        return int(n.value)
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h is not None and h.value:
+            self._lib.pvdb_exchange_destroy(h)
+
+    def __del__(self) -> None:  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def merge_topk_dev(device: int, d_scores: int, d_rows: int, nlists: int, nq: int, k: int, d_out_scores: int,

@@ -3,15 +3,23 @@
 SURVEY.md 8(e): the database rows are split into contiguous, equal blocks (global row r lives on
 rank ``r // rows_per_rank``); every rank holds the full query batch, scans its own shard with the
 same kernels as the single-GPU path and produces a local (Q, k) list whose row indices are already
-global (``row_base``); ONE all-gather of the packed {rows, scores} blocks (Q*k*12 bytes per rank)
-feeds the k-way merge kernel, after which every rank holds the same final (Q, k).  The reference
-has no counterpart (it is single process); the merged result equals what one store holding all
-rows would return.
+global (``row_base``); the per-rank lists are exchanged and k-way merged, after which every rank
+holds the same final (Q, k).  The reference has no counterpart (it is single process); the merged
+result equals what one store holding all rows would return.
+
+The exchange (k <= 128): every rank owns a mailbox in HBM that its peers write over NVLink (CUDA IPC);
+the kernel that finishes a local list stores it into every peer's mailbox, raises a flag, waits for
+the peers' flags and merges -- inside the scan kernel for single queries, one extra kernel after a
+tensor-core batch (csrc/exchange.cuh).  No collective call and no extra launch sits on the query
+path; torch.distributed only carries the one-time handle exchange.  If the mailboxes cannot be set
+up (no peer access), or for k > 128, the round-1 path is used: ONE NCCL all-gather of the packed
+{rows, scores} blocks + the merge kernel.
 
 torch is used here for what it is good at: process-group plumbing, device buffers, streams.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -58,6 +66,61 @@ class ShardedSearch:
         self._host_merge = merge
         local.set_row_base(self.row0)
         self._bufs: dict[tuple, dict[str, torch.Tensor]] = {}
+        self._ex = None            # engine.Exchange once connected
+        self._ex_failed = False    # peer mailboxes unavailable on this box: stay on the NCCL path
+
+    # ------------------------------------------------------------------ peer-memory exchange
+    MAX_EXCHANGE_K = 128
+
+    def _exchange(self, nq: int, k: int):
+        """The connected exchange end sized for nq x k results, or None (use NCCL).  Collective:
+        every rank calls it with the same arguments, so (re)creation happens in lockstep."""
+        if (self.world == 1 or k > self.MAX_EXCHANGE_K or self._ex_failed or self._host_merge is not None
+                or not torch.cuda.is_available() or os.environ.get("PVDB_NO_PEER_EXCHANGE")):
+            return None
+        need = nq * k
+        if self._ex is not None and self._ex.slot_keys >= need:
+            return self._ex
+        from . import _native as N
+        from .engine import Exchange
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        if self._ex is not None:      # outgrown: nobody may still be inside a kernel that uses it
+            self.close()
+        ok, ex = 1, None
+        handle = bytes(N.IPC_HANDLE_BYTES)
+        try:
+            ex = Exchange(dev.index, self.world, self.rank, max(need, 1 << 16))
+            handle = ex.ipc_handle()
+        except Exception:
+            ok = 0
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(dev)
+        everyone = torch.empty(self.world * N.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            try:
+                ex.connect_ipc(everyone.cpu().numpy().tobytes())
+            except Exception:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            if ex is not None:
+                ex.close()
+            self._ex_failed = True
+            return None
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)   # every rank's mailbox is mapped everywhere before the first launch
+        self._ex = ex
+        return ex
+
+    @property
+    def exchange_mode(self) -> str:
+        if self.world == 1:
+            return "none"
+        return "peer-memory mailboxes (fused)" if self._ex is not None else "nccl all-gather + merge kernel"
 
     # ------------------------------------------------------------------ device path
     def _buffers(self, nq: int, k: int, device) -> dict[str, torch.Tensor]:
@@ -88,6 +151,15 @@ class ShardedSearch:
         b = self._buffers(nq, k, d_queries.device)
         stream = torch.cuda.current_stream().cuda_stream
         n_out = nq * k
+        ex = self._exchange(nq, k)
+        if ex is not None:
+            # fused: the kernels exchange the lists over peer memory and write the merged result
+            self.local.search_exchange_dev(
+                ex, d_queries.data_ptr(), nq, k, b["scores"].data_ptr(), b["rows"].data_ptr(),
+                d_prefilter=d_prefilter.data_ptr() if d_prefilter is not None else 0,
+                precision=precision, normalized=normalized, stream=stream, scan_only=scan_only,
+            )
+            return b["scores"], b["rows"]
         loc = b["local"]
         # packed block: rows (int64) first, then scores (fp32)
         self.local.search_dev(
@@ -115,6 +187,10 @@ class ShardedSearch:
         q = np.ascontiguousarray(queries, dtype=np.float32)
         if self._host_merge is None and torch.cuda.is_available():
             nq = q.shape[0]
+            ex = self._exchange(nq, k)
+            if ex is not None:
+                # one C-ABI call: H2D, scan + fused exchange + merge, result written to pinned host memory
+                return self.local.search_exchange(ex, q, k, prefilter=prefilter, precision=precision)
             st = self._staging(nq, k, q.shape[1])
             st["hq"].numpy()[...] = q                       # pinned staging -> async H2D
             st["dq"].copy_(st["hq"], non_blocking=True)
@@ -188,6 +264,16 @@ class ShardedSearch:
         rows = [blk[: n_out * 8].view("<i8").reshape(nq, k) for blk in blocks]
         scores = [blk[n_out * 8 : n_out * 12].view("<f4").reshape(nq, k) for blk in blocks]
         return self._host_merge(scores, rows, k)
+
+    def close(self) -> None:
+        """Collective when an exchange is connected: unmap the peers' mailboxes, barrier, free."""
+        if self._ex is not None:
+            torch.cuda.synchronize()
+            self._ex.disconnect()
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
+            self._ex.close()
+            self._ex = None
 
     def _staging(self, nq: int, k: int, dim: int) -> dict[str, torch.Tensor]:
         """Pinned host + device staging buffers for the host-buffer path, cached per (nq, k)."""
@@ -427,6 +513,7 @@ class ShardedStore:
         return scores, rows, total
 
     def close(self) -> None:
+        self._search.close()
         self.local.close()
 
 

@@ -518,3 +518,32 @@ def test_guard_large_k_slack(store_factory):
     sc, rows = s.search(qn, k, precision="tf32", normalized=True)
     assert s.guard_stats()[0] == 0
     O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+
+
+# ------------------------------------------------------------------ the large-N oracle is itself pinned
+def test_torch_oracle_is_pinned_to_the_numpy_oracle():
+    """tests/_torch_oracle.py (chunked fp32 torch brute force, the expected value at BASELINE's full
+    sizes) against the numpy oracle at 100k rows: same ids, same scores, masks and zero vectors too."""
+    import torch
+
+    from _torch_oracle import TorchOracle
+
+    dim, n, k = 96, 100_000, 25
+    dev = torch.device("cuda", 0)
+    raw = _gauss(n, dim, 101) * np.float32(3.0)
+    raw[17] = 0.0
+    queries = _gauss(9, dim, 102)
+    queries[4] = 0.0
+    active = np.ones(n, bool)
+    active[np.random.default_rng(3).choice(n, n // 4, replace=False)] = False
+    store = O.normalize_rows(raw)
+    qn, _ = O.prepare_queries(queries, dim)
+    for elig in (None, active):
+        orc = TorchOracle(queries, k, dev)
+        for r0 in range(0, n, 30_000):                           # ragged chunks
+            x = torch.from_numpy(raw[r0:r0 + 30_000]).to(dev)
+            e = None if elig is None else torch.from_numpy(elig[r0:r0 + 30_000]).to(dev)
+            orc.update(x, r0, e)
+        got_s, got_r = orc.result()
+        ref_s, ref_r = O.search(store, qn, k, elig)
+        O.compare_topk(got_s, got_r, ref_s, ref_r, rtol=2e-6, atol=1e-6)

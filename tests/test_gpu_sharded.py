@@ -32,7 +32,34 @@ sh = ShardedSearch(st, r0)
 s, r = sh.search(queries, k, precision="f32")
 s1, r1_ = sh.search(queries[:1], k, precision="f32")
 sb, rb = sh.search(queries, k)  # batch path (tf32 + rescoring) per shard, then merge
+mode = sh.exchange_mode
+# the same calls through the round-1 exchange (NCCL all-gather + merge kernel) must give the same bits
+os.environ["PVDB_NO_PEER_EXCHANGE"] = "1"
+s_n, r_n = sh.search(queries, k, precision="f32")
+sb_n, rb_n = sh.search(queries, k)
+del os.environ["PVDB_NO_PEER_EXCHANGE"]
+assert np.array_equal(r, r_n) and np.array_equal(s, s_n), "fused exchange != nccl exchange (scan path)"
+assert np.array_equal(rb, rb_n) and np.array_equal(sb, sb_n), "fused exchange != nccl exchange (batch path)"
+# device-resident entry point, a larger k (four list slots per lane) and many calls in a row (slot parity)
+qd = torch.from_numpy(queries).cuda()
+for kk in (1, 33, 100):
+    for rep in range(3):
+        sd, rd = sh.search_dev(qd, kk, precision="f32", scan_only=True)
+        torch.cuda.synchronize()
+    os.environ["PVDB_NO_PEER_EXCHANGE"] = "1"
+    sd_n, rd_n = sh.search_dev(qd, kk, precision="f32", scan_only=True)
+    torch.cuda.synchronize()
+    del os.environ["PVDB_NO_PEER_EXCHANGE"]
+    assert torch.equal(rd.cpu(), rd_n.cpu()) and torch.equal(sd.cpu(), sd_n.cpu()), f"k={kk}"
+big = rng.standard_normal((700, dim)).astype(np.float32)
+sB, rB = sh.search(big, 10)
+os.environ["PVDB_NO_PEER_EXCHANGE"] = "1"
+sB_n, rB_n = sh.search(big, 10)
+del os.environ["PVDB_NO_PEER_EXCHANGE"]
+assert np.array_equal(rB, rB_n) and np.array_equal(sB, sB_n), "700-query batch"
+sh.close()
 if rank == 0:
+    print("EXCHANGE_MODE", mode)
     store = O.normalize_rows(full)
     qn, _ = O.prepare_queries(queries, dim)
     ref_s, ref_r = O.search(store, qn, k)
