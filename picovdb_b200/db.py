@@ -33,6 +33,8 @@ from typing import Any, Callable, Literal, Optional, Union
 
 import numpy as np
 
+from ._rows import IdMap, RowSeq
+
 Float = np.float32
 ADAPTIVE_BUFFER = 32
 ARGSORT_THRESHOLD = 0.2
@@ -163,9 +165,17 @@ class _ColumnIndex:
         self.dev_slot: Optional[int] = None
         self.dev_rows = 0
         self.dev_dirty: set[int] = set()
-        for row, doc in enumerate(docs):
-            if doc is not None:
-                self.set(row, doc)
+        if isinstance(docs, RowSeq):
+            # bulk rows carry no metadata besides their id: only the explicit rows need a look
+            if key == K_ID and docs.implicit_rows:
+                self.ok = False
+            for row, doc in docs.explicit_items():
+                if doc is not None:
+                    self.set(row, doc)
+        else:
+            for row, doc in enumerate(docs):
+                if doc is not None:
+                    self.set(row, doc)
 
     def _code(self, value: Any, create: bool) -> int:
         """Dictionary code of a STORED value (create=True) or of a filter value (create=False).  An
@@ -241,13 +251,42 @@ class _ColumnIndex:
             return codes == wanted[0]
         return np.isin(codes, np.asarray(wanted, dtype=np.int32))
 
-    def reindex(self, keep: list[int]) -> None:
-        kept = self.codes[np.asarray(keep, dtype=np.int64)] if keep else np.empty(0, np.int32)
+    def reindex(self, keep) -> None:
+        keep = np.asarray(keep, dtype=np.int64)
+        self.resize(int(keep.max()) + 1 if keep.size else 0)
+        kept = self.codes[keep] if keep.size else np.empty(0, np.int32)
         self.codes = np.full(max(len(keep), 16), -1, dtype=np.int32)
         self.codes[: len(keep)] = kept
         self.n = len(keep)
         self.dev_slot, self.dev_rows = None, 0   # compaction drops the device columns
         self.dev_dirty.clear()
+
+
+def _implicit_id(i: int) -> int:
+    return i
+
+
+def _implicit_doc(i: int) -> dict[str, Any]:
+    return {K_ID: i}
+
+
+# bulk stores above this many implicit rows are saved in the compact row-list form (see save())
+COMPACT_ROWS_THRESHOLD = 1_000_000
+
+
+def _rows_to_json(seq: RowSeq):
+    """What save() writes for ``_ids`` / the documents: the reference's plain JSON list
+    (pico_vdb.py:351-371) -- unless the store holds more than COMPACT_ROWS_THRESHOLD bulk rows, whose
+    10^7-10^8 implicit entries are written as ranges (a form only this class reads back)."""
+    if seq.implicit_rows > COMPACT_ROWS_THRESHOLD:
+        return seq.to_compact()
+    return seq[:]
+
+
+def _rows_from_json(obj, make) -> RowSeq:
+    if isinstance(obj, dict) and "picovdb_b200_rows" in obj:
+        return RowSeq.from_compact(make, obj)
+    return RowSeq(make, obj)
 
 
 def _default_engine_factory(dim: int, **kw):
@@ -296,12 +335,15 @@ class PicoVectorDB:
         self._capacity = capacity
         self._precision = precision
 
-        self._ids: list[Any] = []
-        self._docs: list[Optional[dict[str, Any]]] = []
+        # list / dict semantics of the reference's containers (pico_vdb.py:137-143); bulk-ingested rows
+        # are stored as implicit ranges (see _rows.py), so 10^8 rows do not cost 10^8 Python objects
+        self._ids: RowSeq = RowSeq(_implicit_id)
+        self._docs: RowSeq = RowSeq(_implicit_doc)
         self._free: list[int] = []
-        self._id2idx: dict[Any, int] = {}
+        self._id2idx: IdMap = IdMap()
         self._additional: dict[str, Any] = {}
-        self._active_indices: np.ndarray = np.empty(0, dtype=np.int64)
+        self._active_explicit: np.ndarray = np.empty(0, dtype=np.int64)  # rows of explicit ids, insertion order
+        self._auto_hi = 0  # 1 + the largest integer id seen: default ids of upsert_array start no lower
 
         ab_env = os.getenv("PICOVDB_ADAPTIVE_BUFFER")
         thr_env = os.getenv("PICOVDB_ARGSORT_THRESHOLD")
@@ -385,6 +427,28 @@ class PicoVectorDB:
     def _invalidate(self) -> None:
         self._host_cache = None
 
+    def _note_id(self, _id: Any) -> None:
+        if isinstance(_id, (int, np.integer)) and not isinstance(_id, (bool, np.bool_)) and _id >= self._auto_hi:
+            self._auto_hi = int(_id) + 1
+
+    def _default_ids(self, n: int) -> range:
+        """Default ids of a bulk call: n consecutive integers from the slot count upwards, moved past
+        every integer id already seen so that they never collide."""
+        id0 = max(len(self._ids), self._auto_hi)
+        return range(id0, id0 + n)
+
+    @property
+    def _active_indices(self) -> np.ndarray:
+        """Rows of all live records (pico_vdb.py:143).  Explicit rows in insertion order, then the
+        rows of bulk ranges; materialised on demand (O(rows) for a bulk store)."""
+        if self._id2idx.implicit_count == 0:
+            return self._active_explicit
+        return np.concatenate([self._active_explicit, self._id2idx.implicit_rows()])
+
+    @_active_indices.setter
+    def _active_indices(self, value: np.ndarray) -> None:
+        self._active_explicit = np.asarray(value, dtype=np.int64)
+
     # ------------------------------------------------------------------ persistence
     @_timed("load")
     def _load_or_init(self) -> None:
@@ -392,25 +456,42 @@ class PicoVectorDB:
         if os.path.exists(ids_file) and os.path.exists(vecs_file):
             logger.info("Loading existing DB …")
             with open(ids_file, "r", encoding="utf-8") as f:
-                self._ids = json.load(f)
+                self._ids = _rows_from_json(json.load(f), _implicit_id)
             count = len(self._ids)
             vectors = self._read_vectors(vecs_file, count)  # memory-mapped; streamed to the device below
             if os.path.exists(meta_file):
                 with open(meta_file, "r", encoding="utf-8") as f:
                     meta_json = json.load(f)
-                self._docs = meta_json.get("data", [None] * count)
+                self._docs = _rows_from_json(meta_json.get("data", [None] * count), _implicit_doc)
                 self._additional = meta_json.get("additional_data", {})
             else:
-                self._docs = [None] * count
+                self._docs = RowSeq(_implicit_doc, [None] * count)
             active = np.zeros(count, dtype=bool)
-            for i, (_id, doc) in enumerate(zip(self._ids, self._docs)):
+            explicit_rows: list[int] = []
+            implicit = {r0: (n, id0) for r0, n, id0 in self._ids.implicit_ranges()}
+            for r0, n, _ in self._docs.implicit_ranges():
+                # bulk range (compact form only): every row is live unless a later delete overrode it
+                if implicit.get(r0, (None,))[0] != n:
+                    raise ValueError("compact id / document ranges do not line up")
+                self._id2idx.add_range(implicit[r0][1], n, r0)
+                active[r0:r0 + n] = True
+            for row, doc in self._docs.explicit_items():
+                _id = self._ids[row]
+                in_range = bool(active[row])
                 if doc is None:
-                    self._free.append(i)
-                elif _id is not None:
-                    self._id2idx[_id] = i
-            if self._id2idx:
-                self._active_indices = np.fromiter(self._id2idx.values(), dtype=np.int64)
-                active[self._active_indices] = True
+                    self._free.append(row)
+                    if in_range:
+                        self._id2idx.pop(_id, None)
+                        active[row] = False
+                elif _id is not None and not in_range:
+                    self._id2idx[_id] = row
+                    explicit_rows.append(row)
+                    active[row] = True
+            self._active_explicit = np.asarray(explicit_rows, dtype=np.int64)
+            for _, n, id0 in self._ids.implicit_ranges():
+                self._auto_hi = max(self._auto_hi, id0 + n)
+            for _, _id in self._ids.explicit_items():
+                self._note_id(_id)
             # stream the matrix to the device in row blocks (multiples of 32 rows so every block's
             # slice of the active bitmap starts on a word boundary); the file is only mapped, so a
             # store larger than host RAM still loads
@@ -423,8 +504,8 @@ class PicoVectorDB:
         else:
             if self._capacity is not None:
                 cap = int(self._capacity)
-                self._ids = [None] * cap
-                self._docs = [None] * cap
+                self._ids = RowSeq(_implicit_id, [None] * cap)
+                self._docs = RowSeq(_implicit_doc, [None] * cap)
                 # popped from the end, as in the reference; a row-sharded engine supplies an order that
                 # deals the rows out over its shards so a partly filled store is balanced
                 order = getattr(self._engine, "free_order", None)
@@ -466,12 +547,13 @@ class PicoVectorDB:
             try:
                 if writer:
                     with open(tmp_ids, "w", encoding="utf-8") as f:
-                        json.dump(self._ids, f, ensure_ascii=False)
+                        json.dump(_rows_to_json(self._ids), f, ensure_ascii=False)
                 self._write_vectors(tmp_vecs)
                 if writer:
                     with open(tmp_meta, "w", encoding="utf-8") as f:
                         json.dump(
-                            {"embedding_dim": self.dim, "data": self._docs, "additional_data": self._additional},
+                            {"embedding_dim": self.dim, "data": _rows_to_json(self._docs),
+                             "additional_data": self._additional},
                             f,
                             ensure_ascii=False,
                         )
@@ -577,6 +659,7 @@ class PicoVectorDB:
                     if item_id is None:
                         item_id = _hash_vec(_normalize(raw))
                     meta[K_ID] = item_id
+                    self._note_id(item_id)
                     if item_id in self._id2idx:
                         row = self._id2idx[item_id]
                         if row < len(self._docs):
@@ -618,8 +701,8 @@ class PicoVectorDB:
                     self._invalidate()
                 if new_active:
                     add = np.asarray(new_active, dtype=np.int64)
-                    self._active_indices = (
-                        np.append(self._active_indices, add) if self._active_indices.size else add
+                    self._active_explicit = (
+                        np.append(self._active_explicit, add) if self._active_explicit.size else add
                     )
             return report
 
@@ -629,20 +712,61 @@ class PicoVectorDB:
         ids: Optional[list[Any]] = None,
         docs: Optional[list[dict[str, Any]]] = None,
     ) -> list[Any]:
-        """Bulk ingest of NEW records from an (n, dim) array: one staging copy, one device call,
-        no per-item numpy work.  ``ids`` default to consecutive integers continuing from the
-        current slot count; every id must be absent from the DB.  Returns the ids."""
+        """Bulk ingest of NEW records from an (n, dim) array: one device call, no per-item work.
+
+        ``ids`` default to consecutive integers continuing from the current slot count; every id must be
+        absent from the DB.  Without ``ids`` and ``docs`` the rows are *implicit*: no Python object is
+        created per row (``_rows.py``) -- the id of row r is an integer of a range, its document
+        ``{"_id_": id}`` is materialised when a query returns it -- which is what makes 10^7-10^8-row
+        stores usable through this class.  A DB with free slots or ``capacity=`` fills those slots
+        first (explicit bookkeeping).  Returns the ids (a ``range`` for implicit rows)."""
         vecs = _to_c_f32(vectors)
         if vecs.ndim != 2 or vecs.shape[1] != self.dim:
             raise ValueError(f"upsert_array expects shape (n, {self.dim}); got {tuple(vecs.shape)}")
         n = vecs.shape[0]
         with self._rwlock.write_lock():
-            if self._capacity is not None or self._free:
-                raise ValueError("upsert_array appends rows; it needs a DB without free slots or fixed capacity")
-            row0 = len(self._ids)
-            new_ids = list(range(row0, row0 + n)) if ids is None else list(ids)
-            if len(new_ids) != n or (docs is not None and len(docs) != n):
+            if (ids is not None and len(ids) != n) or (docs is not None and len(docs) != n):
                 raise ValueError("ids / docs length does not match the number of vectors")
+            row0 = len(self._ids)
+            if self._capacity is not None or self._free:
+                # slots come from the free list (popped from its end, as upsert does)
+                if self._capacity is not None and n > len(self._free):
+                    raise ValueError("Database capacity exceeded")
+                n_slots = min(n, len(self._free))
+                rows = [self._free.pop() for _ in range(n_slots)] + list(range(row0, row0 + n - n_slots))
+                new_ids = list(self._default_ids(n)) if ids is None else list(ids)
+                if len(set(new_ids)) != n or any(i in self._id2idx for i in new_ids):
+                    self._free.extend(reversed(rows[:n_slots]))
+                    raise ValueError("upsert_array ids must be unique and not present in the DB")
+                self._engine.upsert_rows(vecs, np.asarray(rows, dtype=np.int64))
+                self._invalidate()
+                self._ids.extend([None] * (n - n_slots))
+                self._docs.extend([None] * (n - n_slots))
+                for j, (row, _id) in enumerate(zip(rows, new_ids)):
+                    self._note_id(_id)
+                    self._ids[row] = _id
+                    self._docs[row] = {K_ID: _id} if docs is None else {**docs[j], K_ID: _id}
+                    self._id2idx[_id] = row
+                    for col in self._columns.values():
+                        col.set(row, self._docs[row])
+                add = np.asarray(rows, dtype=np.int64)
+                self._active_explicit = np.append(self._active_explicit, add) if self._active_explicit.size else add
+                return new_ids
+            if ids is None and docs is None:
+                # implicit rows: n consecutive integer ids, no per-row object
+                auto = self._default_ids(n)
+                if self._id2idx.overlaps(auto.start, n):
+                    raise ValueError("upsert_array ids must be unique and not present in the DB")
+                self._engine.upsert_range(vecs, row0)
+                self._invalidate()
+                self._ids.extend_range(auto.start, n)
+                self._docs.extend_range(auto.start, n)
+                self._id2idx.add_range(auto.start, n, row0)
+                self._auto_hi = auto.stop
+                for col in self._columns.values():
+                    col.resize(row0 + n)      # bulk rows carry no metadata: every key reads "absent"
+                return auto  # type: ignore[return-value]
+            new_ids = list(self._default_ids(n)) if ids is None else list(ids)
             if len(set(new_ids)) != n or any(i in self._id2idx for i in new_ids):
                 raise ValueError("upsert_array ids must be unique and not present in the DB")
             self._engine.upsert_range(vecs, row0)
@@ -653,11 +777,13 @@ class PicoVectorDB:
             else:
                 self._docs.extend({**d, K_ID: i} for d, i in zip(docs, new_ids))
             self._id2idx.update(zip(new_ids, range(row0, row0 + n)))
+            for _id in new_ids:
+                self._note_id(_id)
             for col in self._columns.values():
                 for row in range(row0, row0 + n):
                     col.set(row, self._docs[row])
             add = np.arange(row0, row0 + n, dtype=np.int64)
-            self._active_indices = np.append(self._active_indices, add) if self._active_indices.size else add
+            self._active_explicit = np.append(self._active_explicit, add) if self._active_explicit.size else add
             return new_ids
 
     def store_additional_data(self, **kwargs) -> None:
@@ -685,9 +811,9 @@ class PicoVectorDB:
             if rows:
                 self._engine.delete_rows(np.asarray(rows, dtype=np.int64))
                 self._invalidate()
-                if self._active_indices.size:
+                if self._active_explicit.size:
                     gone = np.asarray(rows, dtype=np.int64)
-                    self._active_indices = self._active_indices[~np.isin(self._active_indices, gone)]
+                    self._active_explicit = self._active_explicit[~np.isin(self._active_explicit, gone)]
             return removed
 
     # ------------------------------------------------------------------ search
@@ -936,15 +1062,21 @@ class PicoVectorDB:
         with self._rwlock.write_lock():
             if not self._free:
                 return
-            keep = sorted(self._id2idx.values())
-            self._engine.compact(np.asarray(keep, dtype=np.int64))
+            keep = self._id2idx.sorted_rows()
+            self._engine.compact(keep)
             self._invalidate()
-            self._ids = [self._ids[i] for i in keep]
-            self._docs = [self._docs[i] for i in keep]
+            self._ids = self._ids.take_sorted(keep)      # runs of bulk rows stay implicit ranges
+            self._docs = self._docs.take_sorted(keep)
             for col in self._columns.values():
                 col.reindex(keep)
-            self._id2idx = {_id: i for i, _id in enumerate(self._ids)}
-            self._active_indices = np.arange(len(self._ids), dtype=np.int64)
+            self._id2idx = IdMap()
+            explicit_rows = []
+            for r0, n, id0 in self._ids.implicit_ranges():
+                self._id2idx.add_range(id0, n, r0)
+            for row, _id in self._ids.explicit_items():
+                self._id2idx[_id] = row
+                explicit_rows.append(row)
+            self._active_explicit = np.asarray(explicit_rows, dtype=np.int64)
             self._free = []
 
     def rebuild_index(self) -> None:
