@@ -116,6 +116,11 @@ int pvdb_store_download(pvdb_store_t* s, int64_t row0, int64_t n, float* out);
  * active (rebuild of _active_indices, pico_vdb.py:247-259). */
 int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const float* vecs,
                       const uint32_t* active_bits);
+/* The bf16 mirror as stored: n x dim bf16 bit patterns.  Persists a bf16-only store at half the size of
+ * its fp32 expansion; upload_bf16 is the matching raw load (bf16-only stores). */
+int pvdb_store_download_bf16(pvdb_store_t* s, int64_t row0, int64_t n, uint16_t* out);
+int pvdb_store_upload_bf16(pvdb_store_t* s, int64_t row0, int64_t n, const uint16_t* vecs,
+                           const uint32_t* active_bits);
 /* Copy the active bitmap out: ceil(rows/32) words. */
 int pvdb_store_active_bits(pvdb_store_t* s, uint32_t* out_words);
 /* Compaction: new row i := old row keep_rows[i] (ascending), all n kept rows active, rows := n

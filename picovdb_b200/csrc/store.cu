@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "store.cuh"
@@ -432,7 +433,9 @@ extern "C" int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_
   s->flags = flags;
   s->h_pinned.pinned_host = true;
   s->h_flag.pinned_host = true;
+  s->h_pipe[0].pinned_host = s->h_pipe[1].pinned_host = true;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&s->pipe_ev[b], cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_err_words), 16);
   if (e == cudaSuccess) e = cudaMemset(s->d_err_words, 0, 16);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->order_event, cudaEventDisableTiming);
@@ -465,8 +468,11 @@ extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
   s->active.release();
   s->drop_columns();
   for (Scratch* sc : {&s->d_in, &s->d_rows, &s->d_prefilter, &s->d_qn, &s->d_qn16, &s->d_partial, &s->d_out,
-                      &s->d_misc, &s->h_pinned, &s->d_qeps, &s->d_flag, &s->h_flag, &s->d_xloc})
+                      &s->d_misc, &s->h_pinned, &s->d_qeps, &s->d_flag, &s->h_flag, &s->d_xloc, &s->h_pipe[0],
+                      &s->h_pipe[1]})
     sc->release();
+  for (cudaEvent_t ev : s->pipe_ev)
+    if (ev) cudaEventDestroy(ev);
   if (s->d_err_words) cudaFree(s->d_err_words);
   if (s->order_event) cudaEventDestroy(s->order_event);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -517,6 +523,83 @@ extern "C" int pvdb_store_info(pvdb_store_t* s, pvdb_store_info_t* out) {
   out->active = static_cast<int64_t>(act);
   out->row_base = s->row_base;
   out->device_bytes = s->f32.bytes + s->bf16.bytes + s->active.bytes;
+  return PVDB_OK;
+}
+
+// ---------------------------------------------------------------------------- host <-> device streaming
+static constexpr int64_t kPipeBytes = 32ll << 20;  // per pinned buffer
+
+// memcpy split over a few threads: one core copies ~10 GB/s, PCIe 5 moves ~50 GB/s
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned want = std::min<unsigned>(8, std::max<unsigned>(1, hw / 2));
+  const size_t min_piece = size_t(2) << 20;
+  const unsigned n = static_cast<unsigned>(std::min<size_t>(want, std::max<size_t>(1, bytes / min_piece)));
+  if (n <= 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t piece = ((bytes + n - 1) / n + 63) & ~size_t(63);
+  for (unsigned i = 1; i < n; ++i) {
+    const size_t off = std::min(bytes, piece * i), len = std::min(bytes - off, piece);
+    if (len) th.emplace_back([=]() { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, len); });
+  }
+  std::memcpy(dst, src, std::min(bytes, piece));
+  for (auto& t : th) t.join();
+}
+
+// Host -> device, block by block through the pinned pair.  consume(d_block, first_item, items) enqueues
+// the work that reads the staged block on `st` (it runs after the block's DMA, stream order).
+template <typename F>
+static int stream_h2d(pvdb_store* s, const void* host, int64_t items, size_t item_bytes, int64_t align_items,
+                      cudaStream_t st, F&& consume) {
+  int64_t per = std::max<int64_t>(1, kPipeBytes / static_cast<int64_t>(item_bytes));
+  if (align_items > 1) per = std::max<int64_t>(align_items, per / align_items * align_items);
+  const size_t block_bytes = static_cast<size_t>(std::min(per, items)) * item_bytes;
+  PVDB_TRY(s->h_pipe[0].ensure(block_bytes));
+  if (items > per) PVDB_TRY(s->h_pipe[1].ensure(block_bytes));
+  PVDB_TRY(s->d_in.ensure(block_bytes));
+  int b = 0;
+  for (int64_t i0 = 0; i0 < items; i0 += per, b ^= 1) {
+    const int64_t m = std::min(per, items - i0);
+    const size_t bytes = static_cast<size_t>(m) * item_bytes;
+    PVDB_CUDA(cudaEventSynchronize(s->pipe_ev[b]));  // the DMA that last read this pinned buffer is done
+    parallel_memcpy(s->h_pipe[b].ptr, static_cast<const char*>(host) + static_cast<size_t>(i0) * item_bytes, bytes);
+    PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, s->h_pipe[b].ptr, bytes, cudaMemcpyHostToDevice, st));
+    PVDB_CUDA(cudaEventRecord(s->pipe_ev[b], st));
+    PVDB_TRY(consume(s->d_in.ptr, i0, m));
+  }
+  return PVDB_OK;
+}
+
+// Device -> host: produce(d_block, first_item, items) enqueues the work that fills the device staging
+// block; its DMA into one pinned buffer overlaps the host copy of the previous block out of the other.
+template <typename F>
+static int stream_d2h(pvdb_store* s, void* host, int64_t items, size_t item_bytes, cudaStream_t st, F&& produce) {
+  const int64_t per = std::max<int64_t>(1, kPipeBytes / static_cast<int64_t>(item_bytes));
+  const size_t block_bytes = static_cast<size_t>(std::min(per, items)) * item_bytes;
+  PVDB_TRY(s->h_pipe[0].ensure(block_bytes));
+  if (items > per) PVDB_TRY(s->h_pipe[1].ensure(block_bytes));
+  int b = 0;
+  int64_t prev0 = -1, prev_m = 0;
+  for (int64_t i0 = 0; i0 < items; i0 += per, b ^= 1) {
+    const int64_t m = std::min(per, items - i0);
+    PVDB_TRY(produce(s->h_pipe[b].ptr, i0, m));      // enqueues the D2H into pinned buffer b
+    PVDB_CUDA(cudaEventRecord(s->pipe_ev[b], st));
+    if (prev0 >= 0) {
+      PVDB_CUDA(cudaEventSynchronize(s->pipe_ev[b ^ 1]));
+      parallel_memcpy(static_cast<char*>(host) + static_cast<size_t>(prev0) * item_bytes, s->h_pipe[b ^ 1].ptr,
+                      static_cast<size_t>(prev_m) * item_bytes);
+    }
+    prev0 = i0;
+    prev_m = m;
+  }
+  if (prev0 >= 0) {
+    PVDB_CUDA(cudaEventSynchronize(s->pipe_ev[b ^ 1]));
+    parallel_memcpy(static_cast<char*>(host) + static_cast<size_t>(prev0) * item_bytes, s->h_pipe[b ^ 1].ptr,
+                    static_cast<size_t>(prev_m) * item_bytes);
+  }
   return PVDB_OK;
 }
 
@@ -571,14 +654,12 @@ extern "C" int pvdb_store_upsert_range(pvdb_store_t* s, const float* vecs, int64
   cudaStream_t st = s->stream;
   PVDB_TRY(s->use_stream(st));
   PVDB_TRY(s->ensure_capacity(row0 + n, st));
-  const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
-  PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
-  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
-    const int64_t m = std::min(chunk, n - i0);
-    PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, vecs + i0 * s->dim, static_cast<size_t>(m) * s->dim * sizeof(float),
-                              cudaMemcpyHostToDevice, st));
-    PVDB_TRY(upsert_device(s, static_cast<const float*>(s->d_in.ptr), nullptr, row0 + i0, m, row0 + i0 + m - 1, st));
-  }
+  // pinned double buffering: the host copy of block i+1 overlaps the DMA + kernel of block i
+  PVDB_TRY(stream_h2d(s, vecs, n, static_cast<size_t>(s->dim) * sizeof(float), 1, st,
+                      [&](void* d_block, int64_t i0, int64_t m) {
+                        return upsert_device(s, static_cast<const float*>(d_block), nullptr, row0 + i0, m,
+                                             row0 + i0 + m - 1, st);
+                      }));
   PVDB_CUDA(cudaStreamSynchronize(st));
   return PVDB_OK;
 }
@@ -660,24 +741,45 @@ extern "C" int pvdb_store_download(pvdb_store_t* s, int64_t row0, int64_t n, flo
                 (long long)(row0 + n), (long long)s->rows);
   cudaStream_t st = s->stream;
   PVDB_TRY(s->use_stream(st));
-  if (s->f32.ptr) {
-    const float* src = static_cast<const float*>(s->f32.ptr) + row0 * s->ld_f32;
-    PVDB_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(s->dim) * 4, src, static_cast<size_t>(s->ld_f32) * 4,
-                                static_cast<size_t>(s->dim) * 4, static_cast<size_t>(n), cudaMemcpyDeviceToHost, st));
-  } else {
-    const int64_t chunk = std::max<int64_t>(1, kStageBytes / (static_cast<int64_t>(s->dim) * 4));
-    PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min(chunk, n)) * s->dim * sizeof(float)));
-    for (int64_t i0 = 0; i0 < n; i0 += chunk) {
-      const int64_t m = std::min(chunk, n - i0);
+  // streamed through the pinned pair: the DMA of block i+1 overlaps the host copy of block i into the
+  // caller's buffer (a memory-mapped .npy file in save(), pico_vdb.py:356)
+  const size_t row_bytes = static_cast<size_t>(s->dim) * sizeof(float);
+  if (!s->f32.ptr) PVDB_TRY(s->d_in.ensure(static_cast<size_t>(std::min<int64_t>(n, kPipeBytes / row_bytes + 1)) * row_bytes));
+  PVDB_TRY(stream_d2h(s, out, n, row_bytes, st, [&](void* pinned, int64_t i0, int64_t m) -> int {
+    if (s->f32.ptr) {
+      const float* src = static_cast<const float*>(s->f32.ptr) + (row0 + i0) * s->ld_f32;
+      PVDB_CUDA(cudaMemcpy2DAsync(pinned, row_bytes, src, static_cast<size_t>(s->ld_f32) * 4, row_bytes,
+                                  static_cast<size_t>(m), cudaMemcpyDeviceToHost, st));
+    } else {
       gather_rows_kernel<<<warp_grid(m), 256, 0, st>>>(nullptr, row0 + i0, m, s->dim, nullptr, s->ld_f32,
                                                        static_cast<const __nv_bfloat16*>(s->bf16.ptr), s->ld_bf16,
                                                        static_cast<float*>(s->d_in.ptr));
       PVDB_LAUNCH_CHECK();
-      PVDB_CUDA(cudaMemcpyAsync(out + i0 * s->dim, s->d_in.ptr, static_cast<size_t>(m) * s->dim * sizeof(float),
-                                cudaMemcpyDeviceToHost, st));
+      PVDB_CUDA(cudaMemcpyAsync(pinned, s->d_in.ptr, static_cast<size_t>(m) * row_bytes, cudaMemcpyDeviceToHost, st));
     }
-  }
-  PVDB_CUDA(cudaStreamSynchronize(st));
+    return PVDB_OK;
+  }));
+  return PVDB_OK;
+}
+
+// The bf16 mirror as it is: n x dim bf16 (uint16 bit patterns), for persisting a bf16-only store at half
+// the size of its fp32 expansion.
+extern "C" int pvdb_store_download_bf16(pvdb_store_t* s, int64_t row0, int64_t n, uint16_t* out) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!s->bf16.ptr) return fail(PVDB_ERR_UNSUPPORTED, "download_bf16: this store keeps no bf16 mirror");
+  if (!out || n < 0 || row0 < 0 || row0 + n > s->rows)
+    return fail(PVDB_ERR_INVALID, "download_bf16: range [%lld, %lld) outside [0, %lld)", (long long)row0,
+                (long long)(row0 + n), (long long)s->rows);
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  const size_t row_bytes = static_cast<size_t>(s->dim) * sizeof(uint16_t);
+  PVDB_TRY(stream_d2h(s, out, n, row_bytes, st, [&](void* pinned, int64_t i0, int64_t m) -> int {
+    const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(s->bf16.ptr) + (row0 + i0) * s->ld_bf16;
+    PVDB_CUDA(cudaMemcpy2DAsync(pinned, row_bytes, src, static_cast<size_t>(s->ld_bf16) * 2, row_bytes,
+                                static_cast<size_t>(m), cudaMemcpyDeviceToHost, st));
+    return PVDB_OK;
+  }));
   return PVDB_OK;
 }
 
@@ -691,19 +793,13 @@ extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const
   cudaStream_t st = s->stream;
   PVDB_TRY(s->use_stream(st));
   PVDB_TRY(s->ensure_capacity(row0 + n, st));
-  const int64_t chunk = std::max<int64_t>(32, (kStageBytes / (static_cast<int64_t>(s->dim) * 4)) & ~int64_t(31));
-  for (int64_t i0 = 0; i0 < n; i0 += chunk) {
-    const int64_t m = std::min(chunk, n - i0);
-    const float* src = vecs + i0 * s->dim;
-    const float* dense = nullptr;
+  const size_t row_bytes = static_cast<size_t>(s->dim) * sizeof(float);
+  PVDB_TRY(stream_h2d(s, vecs, n, row_bytes, 32, st, [&](void* d_block, int64_t i0, int64_t m) -> int {
+    const float* dense = static_cast<const float*>(d_block);
     if (s->f32.ptr) {
       float* dst = static_cast<float*>(s->f32.ptr) + (row0 + i0) * s->ld_f32;
-      PVDB_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(s->ld_f32) * 4, src, static_cast<size_t>(s->dim) * 4,
-                                  static_cast<size_t>(s->dim) * 4, static_cast<size_t>(m), cudaMemcpyHostToDevice, st));
-    } else {
-      PVDB_TRY(s->d_in.ensure(static_cast<size_t>(m) * s->dim * sizeof(float)));
-      PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, src, static_cast<size_t>(m) * s->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-      dense = static_cast<const float*>(s->d_in.ptr);
+      PVDB_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(s->ld_f32) * 4, dense, row_bytes, row_bytes,
+                                  static_cast<size_t>(m), cudaMemcpyDeviceToDevice, st));
     }
     if (s->bf16.ptr) {
       mirror_rows_kernel<<<warp_grid(m), 256, 0, st>>>(dense, s->dim, static_cast<const float*>(s->f32.ptr), s->ld_f32,
@@ -715,7 +811,8 @@ extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const
                                                      row0 + i0, m, s->d_err_words);
       PVDB_LAUNCH_CHECK();
     }
-  }
+    return PVDB_OK;
+  }));
   const uint32_t* d_bits = nullptr;
   if (active_bits) {
     const size_t nwords = static_cast<size_t>((n + 31) >> 5);
@@ -729,6 +826,42 @@ extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const
     set_active_range_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(s->active.ptr), row0, n, d_bits);
     PVDB_LAUNCH_CHECK();
   }
+  s->rows = std::max(s->rows, row0 + n);
+  PVDB_CUDA(cudaStreamSynchronize(st));
+  return PVDB_OK;
+}
+
+// Raw load of bf16 rows (what pvdb_store_download_bf16 wrote) into a bf16-only store.
+extern "C" int pvdb_store_upload_bf16(pvdb_store_t* s, int64_t row0, int64_t n, const uint16_t* vecs,
+                                      const uint32_t* active_bits) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!s->bf16.ptr && s->capacity > 0) return fail(PVDB_ERR_UNSUPPORTED, "upload_bf16: this store keeps no bf16 mirror");
+  if (s->flags & PVDB_STORE_F32)
+    return fail(PVDB_ERR_UNSUPPORTED, "upload_bf16: the store keeps an fp32 matrix; load fp32 rows instead");
+  if (!vecs || n < 0 || row0 < 0 || row0 + n - 1 > 0xfffffffell) return fail(PVDB_ERR_INVALID, "upload_bf16: bad arguments");
+  if (active_bits && (row0 & 31)) return fail(PVDB_ERR_INVALID, "upload_bf16: row0 must be a multiple of 32 with active_bits");
+  cudaStream_t st = s->stream;
+  PVDB_TRY(s->use_stream(st));
+  PVDB_TRY(s->ensure_capacity(row0 + n, st));
+  const size_t row_bytes = static_cast<size_t>(s->dim) * sizeof(uint16_t);
+  PVDB_TRY(stream_h2d(s, vecs, n, row_bytes, 32, st, [&](void* d_block, int64_t i0, int64_t m) -> int {
+    __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(s->bf16.ptr) + (row0 + i0) * s->ld_bf16;
+    PVDB_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(s->ld_bf16) * 2, d_block, row_bytes, row_bytes,
+                                static_cast<size_t>(m), cudaMemcpyDeviceToDevice, st));
+    return PVDB_OK;
+  }));
+  const uint32_t* d_bits = nullptr;
+  if (active_bits) {
+    const size_t nwords = static_cast<size_t>((n + 31) >> 5);
+    PVDB_TRY(s->d_prefilter.ensure(nwords * sizeof(uint32_t)));
+    PVDB_CUDA(cudaMemcpyAsync(s->d_prefilter.ptr, active_bits, nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    d_bits = static_cast<const uint32_t*>(s->d_prefilter.ptr);
+  }
+  const int64_t nwords = ((row0 + n + 31) >> 5) - (row0 >> 5);
+  const int blocks = static_cast<int>(std::min<int64_t>((nwords + 255) / 256, kNumSMs * 8));
+  set_active_range_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t*>(s->active.ptr), row0, n, d_bits);
+  PVDB_LAUNCH_CHECK();
   s->rows = std::max(s->rows, row0 + n);
   PVDB_CUDA(cudaStreamSynchronize(st));
   return PVDB_OK;

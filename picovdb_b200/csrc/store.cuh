@@ -81,6 +81,10 @@ struct pvdb_store {
   pvdb::Scratch h_pinned;   // pinned bounce buffer for results
   pvdb::Scratch d_qeps;     // per query: ||q - tf32(q)||, ||q - bf16(q)|| (exactness guard of the tensor paths)
   pvdb::Scratch d_flag;     // guard: [count][flagged query indices]
+  // Host <-> device streaming (bulk ingest, load, save): two pinned buffers; the host-side copy of
+  // block i+1 (several threads) overlaps the DMA of block i.  pipe_ev[b] = last DMA that used pin[b].
+  pvdb::Scratch h_pipe[2];
+  cudaEvent_t pipe_ev[2] = {nullptr, nullptr};
   pvdb::Scratch d_xloc;     // this shard's lists before the cross-GPU exchange: [nq*k] rows, then scores
   pvdb::Scratch h_flag;     // pinned copy of d_flag
   // Largest input-rounding error over the rows ever written, as the uint image of two non-negative

@@ -61,6 +61,12 @@ def _vecs_path(base: str) -> str:
     return f"{base}.vecs.npy"
 
 
+def _vecs16_path(base: str) -> str:
+    """bf16 bit patterns of a bf16-only store, (rows, dim) uint16 in .npy framing -- half the size of
+    the fp32 expansion; written instead of ``.vecs.npy`` unless ``save_dtype="f32"``."""
+    return f"{base}.vecs.bf16.npy"
+
+
 def _hash_vec(v: np.ndarray) -> str:
     return hashlib.md5(v.tobytes()).hexdigest()
 
@@ -326,6 +332,7 @@ class PicoVectorDB:
         bf16_mirror: bool = False,
         keep_f32: bool = True,
         precision: str = "auto",
+        save_dtype: Optional[str] = None,
     ) -> None:
         self._rwlock = _RWLock()
         self.dim = int(embedding_dim)
@@ -334,6 +341,9 @@ class PicoVectorDB:
         self._use_memmap = use_memmap
         self._capacity = capacity
         self._precision = precision
+        if save_dtype not in (None, "f32", "bf16"):
+            raise ValueError("save_dtype must be None, 'f32' or 'bf16'")
+        self._save_dtype = save_dtype
 
         # list / dict semantics of the reference's containers (pico_vdb.py:137-143); bulk-ingested rows
         # are stored as implicit ranges (see _rows.py), so 10^8 rows do not cost 10^8 Python objects
@@ -376,7 +386,8 @@ class PicoVectorDB:
         self._device = device
         # the reference ignores capacity= when it loads existing files (pico_vdb.py:227-284): only a
         # fresh DB is pinned to its pre-allocation
-        loading = os.path.exists(_ids_path(storage_file)) and os.path.exists(_vecs_path(storage_file))
+        loading = os.path.exists(_ids_path(storage_file)) and (
+            os.path.exists(_vecs_path(storage_file)) or os.path.exists(_vecs16_path(storage_file)))
         factory = type(self)._engine_factory
         if devices is not None and len(devices) > 1:
             # one process, several GPUs: rows sharded over `devices`, searches merged over NVLink
@@ -453,12 +464,21 @@ class PicoVectorDB:
     @_timed("load")
     def _load_or_init(self) -> None:
         ids_file, vecs_file, meta_file = _ids_path(self._path), _vecs_path(self._path), _meta_path(self._path)
-        if os.path.exists(ids_file) and os.path.exists(vecs_file):
+        vecs16_file = _vecs16_path(self._path)
+        # a bf16-only store reads its own bf16 file when there is one (no fp32 detour, half the bytes)
+        use16 = os.path.exists(vecs16_file) and getattr(self._engine, "bf16_only", False) and (
+            not os.path.exists(vecs_file) or os.path.getmtime(vecs16_file) >= os.path.getmtime(vecs_file))
+        if os.path.exists(ids_file) and (use16 or os.path.exists(vecs_file)):
             logger.info("Loading existing DB …")
             with open(ids_file, "r", encoding="utf-8") as f:
                 self._ids = _rows_from_json(json.load(f), _implicit_id)
             count = len(self._ids)
-            vectors = self._read_vectors(vecs_file, count)  # memory-mapped; streamed to the device below
+            if use16:
+                vectors = np.load(vecs16_file, mmap_mode="r")
+                if vectors.shape != (count, self.dim) or vectors.dtype != np.uint16:
+                    raise ValueError(f"stored bf16 matrix has shape {vectors.shape}, expected ({count}, {self.dim})")
+            else:
+                vectors = self._read_vectors(vecs_file, count)  # memory-mapped; streamed to the device below
             if os.path.exists(meta_file):
                 with open(meta_file, "r", encoding="utf-8") as f:
                     meta_json = json.load(f)
@@ -495,11 +515,14 @@ class PicoVectorDB:
             # stream the matrix to the device in row blocks (multiples of 32 rows so every block's
             # slice of the active bitmap starts on a word boundary); the file is only mapped, so a
             # store larger than host RAM still loads
-            step = max(32, ((64 << 20) // (self.dim * 4)) // 32 * 32)
+            # (inside one call the library streams through pinned double buffers: the host copy of block
+            # i+1 -- the page faults of the mapped file -- overlaps the DMA of block i)
+            step = max(32, ((512 << 20) // (self.dim * 4)) // 32 * 32)
+            put = self._engine.upload_bf16 if use16 else self._engine.upload
             for r0 in range(0, count, step):
                 r1 = min(count, r0 + step)
                 # the slice stays a lazy view of the mapped file: a sharded engine only reads its own rows
-                self._engine.upload(vectors[r0:r1], r0, active[r0:r1])
+                put(vectors[r0:r1], r0, active[r0:r1])
             logger.info("Loaded %d active / %d total vectors", len(self._id2idx), count)
         else:
             if self._capacity is not None:
@@ -537,6 +560,13 @@ class PicoVectorDB:
         """Persist atomically: temp files first, then ``os.replace`` (pico_vdb.py:330-393)."""
         with self._rwlock.write_lock():
             ids_file, vecs_file, meta_file = _ids_path(self._path), _vecs_path(self._path), _meta_path(self._path)
+            # a bf16-only store persists its mirror as it is unless the reference's fp32 file is asked for
+            as16 = self._save_dtype == "bf16" or (self._save_dtype is None and getattr(self._engine, "bf16_only", False))
+            if as16 and not hasattr(self._engine, "download_bf16"):
+                as16 = False
+            stale_vecs = vecs_file if as16 else _vecs16_path(self._path)
+            if as16:
+                vecs_file = _vecs16_path(self._path)
             tmp_ids = f"{ids_file}.tmp"
             tmp_vecs_base = f"{self._path}.vecs.tmp"
             tmp_vecs = f"{tmp_vecs_base}.npy"
@@ -548,7 +578,7 @@ class PicoVectorDB:
                 if writer:
                     with open(tmp_ids, "w", encoding="utf-8") as f:
                         json.dump(_rows_to_json(self._ids), f, ensure_ascii=False)
-                self._write_vectors(tmp_vecs)
+                self._write_vectors(tmp_vecs, as16)
                 if writer:
                     with open(tmp_meta, "w", encoding="utf-8") as f:
                         json.dump(
@@ -560,6 +590,8 @@ class PicoVectorDB:
                     os.replace(tmp_ids, ids_file)
                     os.replace(tmp_vecs, vecs_file)
                     os.replace(tmp_meta, meta_file)
+                    if os.path.exists(stale_vecs):   # the other precision's file would describe an older state
+                        os.remove(stale_vecs)
                     logger.info("Saved %d vectors", len(self._ids))
                 self._engine_barrier()
             finally:
@@ -570,31 +602,45 @@ class PicoVectorDB:
                         except OSError:
                             pass
 
-    def _write_vectors(self, path: str) -> None:
+    def _write_vectors(self, path: str, as16: bool = False) -> None:
         """Write the ``.npy`` file (same header as ``np.save``) in row blocks straight from the
-        device, so saving never needs a second full copy of the matrix in host memory."""
+        device into the mapped file, so saving never needs a second full copy of the matrix in host
+        memory; inside one block the library overlaps the device->host DMA with the copy into the file
+        (pinned double buffers).  ``as16``: the bf16 mirror's bit patterns (uint16) instead of fp32."""
         n = len(self._ids)
         eng = self._engine
         writer = getattr(eng, "is_writer", True)
         sharded = hasattr(eng, "owned_rows")
-        if n == 0 or (self._host_cache is not None and not sharded):
+        if not as16 and (n == 0 or (self._host_cache is not None and not sharded)):
             with open(path, "wb") as f:
                 np.save(f, self._vectors)
             return
         from numpy.lib.format import open_memmap
 
+        dtype = np.uint16 if as16 else Float
+        if n == 0:
+            with open(path, "wb") as f:
+                np.save(f, np.empty((0, self.dim), dtype=dtype))
+            return
         # the writer creates the file (header + size); with a sharded engine the other ranks then map
         # it and every rank stores the rows it owns
-        out = open_memmap(path, mode="w+", dtype=Float, shape=(n, self.dim)) if writer else None
+        out = open_memmap(path, mode="w+", dtype=dtype, shape=(n, self.dim)) if writer else None
         self._engine_barrier()
         if out is None:
             out = open_memmap(path, mode="r+")
         lo, hi = eng.owned_rows() if sharded else (0, n)
         lo, hi = max(lo, 0), min(hi, n)
-        step = max(1, (64 << 20) // (self.dim * 4))
+        step = max(1, (512 << 20) // (self.dim * out.dtype.itemsize))
+        direct = getattr(eng, "download_into", False)  # DeviceStore: stream straight into the mapped file
         for r0 in range(lo, hi, step):
             r1 = min(hi, r0 + step)
-            out[r0:r1] = self._download(r0, r1 - r0)
+            have = max(0, min(r1, int(eng.rows)) - r0) if direct else 0
+            if direct and have == r1 - r0:
+                (eng.download_bf16 if as16 else eng.download)(r0, r1 - r0, out=out[r0:r1])
+            elif as16:
+                out[r0:r1] = eng.download_bf16(r0, r1 - r0)
+            else:
+                out[r0:r1] = self._download(r0, r1 - r0)
         out.flush()
         del out
         self._engine_barrier()
@@ -1038,7 +1084,7 @@ class PicoVectorDB:
             active = len(self._id2idx)
             total = len(self._ids)
             sizes = {}
-            for fn in (_ids_path, _meta_path, _vecs_path):
+            for fn in (_ids_path, _meta_path, _vecs_path, _vecs16_path):
                 p = fn(self._path)
                 try:
                     if os.path.exists(p):

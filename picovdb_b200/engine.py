@@ -46,6 +46,8 @@ def unpack_row_mask(words: np.ndarray, n: int) -> np.ndarray:
 class DeviceStore:
     """Owns one native store on one GPU."""
 
+    download_into = True  # download(..., out=) streams into a caller-provided (mapped) array
+
     def __init__(
         self,
         dim: int,
@@ -63,6 +65,7 @@ class DeviceStore:
         N.check(self._lib.pvdb_store_create(C.byref(h), int(device), int(dim), int(reserve_rows), flags))
         self._h = h
         self._owned = True
+        self.bf16_only = bool(bf16_mirror and not keep_f32)
         self.dim = int(dim)
         self.device = int(device)
 
@@ -75,6 +78,8 @@ class DeviceStore:
         self._owned = False
         self.dim = int(dim)
         self.device = int(device)
+        info = self.info()
+        self.bf16_only = bool(info.flags & N.STORE_BF16) and not (info.flags & N.STORE_F32)
         return self
 
     # -- lifecycle ---------------------------------------------------------------------------
@@ -164,12 +169,36 @@ class DeviceStore:
         N.check(self._lib.pvdb_store_fetch(self.handle, _ptr(rows), rows.shape[0], _ptr(out)))
         return out
 
-    def download(self, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+    def download(self, row0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Rows as fp32.  ``out``: a C-contiguous (n, dim) float32 destination (e.g. a slice of a
+        memory-mapped .npy file) that the rows are streamed into directly."""
         if n is None:
             n = self.rows - row0
-        out = np.empty((n, self.dim), dtype=np.float32)
+        if out is None:
+            out = np.empty((n, self.dim), dtype=np.float32)
+        elif out.shape != (n, self.dim) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("download(out=...) needs a C-contiguous float32 (n, dim) array")
         N.check(self._lib.pvdb_store_download(self.handle, int(row0), int(n), _ptr(out)))
         return out
+
+    def download_bf16(self, row0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Rows of the bf16 mirror as stored: (n, dim) uint16 bit patterns."""
+        if n is None:
+            n = self.rows - row0
+        if out is None:
+            out = np.empty((n, self.dim), dtype=np.uint16)
+        elif out.shape != (n, self.dim) or out.dtype != np.uint16 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("download_bf16(out=...) needs a C-contiguous uint16 (n, dim) array")
+        N.check(self._lib.pvdb_store_download_bf16(self.handle, int(row0), int(n), _ptr(out)))
+        return out
+
+    def upload_bf16(self, vecs16: np.ndarray, row0: int = 0, active: Optional[np.ndarray] = None) -> None:
+        """Raw load of bf16 bit patterns into a bf16-only store."""
+        v = np.ascontiguousarray(vecs16, dtype=np.uint16)
+        if v.ndim != 2 or v.shape[1] != self.dim:
+            raise ValueError(f"upload_bf16 expects (n, {self.dim}) uint16 rows")
+        bits = None if active is None else pack_row_mask(active)
+        N.check(self._lib.pvdb_store_upload_bf16(self.handle, int(row0), v.shape[0], _ptr(v), _ptr(bits)))
 
     def active_mask(self) -> np.ndarray:
         n = self.rows

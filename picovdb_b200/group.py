@@ -51,6 +51,7 @@ class GroupStore:
         self.shards = [DeviceStore.from_handle(C.c_void_p(self._lib.pvdb_group_store(h, i)), dim, d)
                        for i, d in enumerate(devices)]
         self._rows = 0
+        self.bf16_only = bool(bf16_mirror and not keep_f32)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -171,6 +172,27 @@ class GroupStore:
             a, b = max(row0, lo), min(row0 + n, hi, lo + self.shards[i].rows)
             if b > a:
                 out[a - row0: b - row0] = self.shards[i].download(a - lo, b - a)
+        return out
+
+    def upload_bf16(self, vecs16: np.ndarray, row0: int = 0, active: Optional[np.ndarray] = None) -> None:
+        n = len(vecs16)
+        for i in range(self.world):
+            lo, hi = self.shard_bounds(i)
+            a, b = max(row0, lo), min(row0 + n, hi)
+            if b > a:
+                act = None if active is None else np.asarray(active, dtype=bool)[a - row0: b - row0]
+                self.shards[i].upload_bf16(np.ascontiguousarray(vecs16[a - row0: b - row0]), a - lo, act)
+        self._rows = max(self._rows, row0 + n)
+
+    def download_bf16(self, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self._rows - row0
+        out = np.zeros((n, self.dim), dtype=np.uint16)
+        for i in range(self.world):
+            lo, hi = self.shard_bounds(i)
+            a, b = max(row0, lo), min(row0 + n, hi, lo + self.shards[i].rows)
+            if b > a:
+                out[a - row0: b - row0] = self.shards[i].download_bf16(a - lo, b - a)
         return out
 
     def active_mask(self) -> np.ndarray:

@@ -326,6 +326,7 @@ class ShardedStore:
             from .engine import DeviceStore as local_factory  # noqa: N813
         self.local = local_factory(self.dim, device=device, reserve_rows=max(self.row1 - self.row0, 1),
                                    keep_f32=keep_f32, bf16_mirror=bf16_mirror, fixed_capacity=fixed_capacity)
+        self.bf16_only = bool(getattr(self.local, "bf16_only", False))
         self._search = ShardedSearch(self.local, self.row0, group=group, merge=merge)
         self._host_only = merge is not None
         self._rows = 0  # global high-water mark (the same on every rank)
@@ -411,6 +412,25 @@ class ShardedStore:
             a = None if active is None else np.asarray(active, dtype=bool)[lo - row0: hi - row0]
             self.local.upload(np.ascontiguousarray(vecs[lo - row0: hi - row0], dtype=np.float32), lo - self.row0, a)
         self._rows = max(self._rows, row0 + n)
+
+    def upload_bf16(self, vecs16: np.ndarray, row0: int = 0, active: Optional[np.ndarray] = None) -> None:
+        n = len(vecs16)
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1)
+        if hi > lo:
+            a = None if active is None else np.asarray(active, dtype=bool)[lo - row0: hi - row0]
+            self.local.upload_bf16(np.ascontiguousarray(vecs16[lo - row0: hi - row0]), lo - self.row0, a)
+        self._rows = max(self._rows, row0 + n)
+
+    def download_bf16(self, row0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """This rank's part of rows [row0, row0 + n) of the mirror; rows of other ranks read as zeros
+        (save() asks every rank for its own rows only)."""
+        if n is None:
+            n = self._rows - row0
+        out = np.zeros((n, self.dim), dtype=np.uint16)
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1, self.row0 + self.local.rows)
+        if hi > lo:
+            out[lo - row0: hi - row0] = self.local.download_bf16(lo - self.row0, hi - lo)
+        return out
 
     def compact(self, keep_rows: np.ndarray) -> None:
         """Global compaction: new row j <- old row keep[j] (keep ascending, so keep[j] >= j and moving

@@ -547,3 +547,69 @@ def test_torch_oracle_is_pinned_to_the_numpy_oracle():
         got_s, got_r = orc.result()
         ref_s, ref_r = O.search(store, qn, k, elig)
         O.compare_topk(got_s, got_r, ref_s, ref_r, rtol=2e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------ streamed persistence (8(f) row 3)
+def test_streamed_download_upload_roundtrip_and_bf16_file(store_factory, tmp_path):
+    """Multi-block pinned pipelines (rows chosen so several 32 MiB blocks and a ragged tail occur):
+    download == what was uploaded, download(out=memmap) writes the mapped file, and the bf16 bit
+    patterns of a bf16-only store round-trip through download_bf16 / upload_bf16 exactly."""
+    from numpy.lib.format import open_memmap
+
+    dim, n = 256, 100_003           # 102 MB of fp32 rows: four pipeline blocks
+    raw = _gauss(n, dim, 111)
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(raw, 0)                                 # streamed H2D + fused normalise
+    want = O.normalize_rows(raw)
+    got = s.download()
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+    mm = open_memmap(str(tmp_path / "m.npy"), mode="w+", dtype=np.float32, shape=(n, dim))
+    s.download(0, n, out=mm)
+    mm.flush()
+    np.testing.assert_array_equal(np.load(str(tmp_path / "m.npy")), got)
+    active = np.ones(n, bool)
+    active[::3] = False
+    t = store_factory(dim)
+    t.upload(got, 0, active)                               # streamed raw load
+    np.testing.assert_array_equal(t.download(), got)
+    np.testing.assert_array_equal(t.active_mask(), active)
+    b = store_factory(dim, keep_f32=False, bf16_mirror=True)
+    b.upsert_range(raw, 0)
+    bits = b.download_bf16()
+    assert bits.dtype == np.uint16 and bits.shape == (n, dim)
+    as_f32 = (bits.astype(np.uint32) << 16).view(np.float32)
+    np.testing.assert_array_equal(as_f32, b.download())
+    np.testing.assert_allclose(as_f32, want, rtol=8e-3, atol=1e-3)
+    c = store_factory(dim, keep_f32=False, bf16_mirror=True)
+    c.upload_bf16(bits, 0, active)
+    np.testing.assert_array_equal(c.download_bf16(), bits)
+    np.testing.assert_array_equal(c.active_mask(), active)
+    q = _gauss(3, dim, 112)
+    np.testing.assert_array_equal(c.search(q, 5, prefilter=None)[1], b.search(q, 5, prefilter=active)[1])
+    with pytest.raises(Exception):
+        s.upload_bf16(bits[:32], 0)                        # a store with fp32 rows loads fp32
+
+
+def test_bf16_only_db_saves_and_loads_its_mirror(tmp_path):
+    from picovdb_b200 import K_ID, K_VECTOR, PicoVectorDB
+
+    dim, n = 32, 3000
+    vecs = _gauss(n, dim, 113)
+    path = str(tmp_path / "b16")
+    db = PicoVectorDB(embedding_dim=dim, storage_file=path, keep_f32=False, bf16_mirror=True)
+    db.upsert([{K_VECTOR: vecs[i], K_ID: f"r{i}"} for i in range(n)])
+    db.delete(["r5"])
+    want = [r[K_ID] for r in db.query(vecs[7], top_k=5)]
+    db.save()
+    assert os.path.exists(path + ".vecs.bf16.npy") and not os.path.exists(path + ".vecs.npy")
+    assert os.path.getsize(path + ".vecs.bf16.npy") < n * dim * 2 + 1024
+    again = PicoVectorDB(embedding_dim=dim, storage_file=path, keep_f32=False, bf16_mirror=True)
+    assert [r[K_ID] for r in again.query(vecs[7], top_k=5)] == want and len(again) == n - 1
+    np.testing.assert_array_equal(again._vectors, db._vectors)
+    again.close()
+    db.close()
+    ref = PicoVectorDB(embedding_dim=dim, storage_file=path, keep_f32=False, bf16_mirror=True, save_dtype="f32")
+    ref.save()                                             # the reference's fp32 .npy on request
+    assert os.path.exists(path + ".vecs.npy") and not os.path.exists(path + ".vecs.bf16.npy")
+    assert np.load(path + ".vecs.npy").shape == (n, dim)
+    ref.close()

@@ -68,6 +68,34 @@ def main():
              vec_per_s=n / t_bulk, gb_per_s=vecs.nbytes / t_bulk / 1e9)
         db3.close()
 
+    # larger stores: bulk ingest, streamed save and load -- GB/s on the
+    # vector bytes, files on the box's local disk (tmpdir)
+    n2, dim2 = 4_000_000, 384
+    big = np.random.default_rng(2).standard_normal((n2, dim2), dtype=np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        for label, kw, bytes_per in (("fp32 store", {}, 4), ("bf16-only store", {"keep_f32": False, "bf16_mirror": True}, 2)):
+            path = os.path.join(tmp, "big" + str(bytes_per))
+            db = PicoVectorDB(embedding_dim=dim2, storage_file=path, **kw)
+            db.upsert_array(big[:1000])     # warm the pinned buffers / kernels
+            t0 = time.perf_counter()
+            db.upsert_array(big[1000:])
+            t_in = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            db.save()
+            t_save = time.perf_counter() - t0
+            db.close()
+            t0 = time.perf_counter()
+            db = PicoVectorDB(embedding_dim=dim2, storage_file=path, **kw)
+            t_load = time.perf_counter() - t0
+            assert len(db) == n2
+            file_bytes = n2 * dim2 * bytes_per
+            emit(case=f"{label}: upsert_array / save / load of {n2} x {dim2}",
+                 ingest_s=t_in, ingest_gb_per_s=big[1000:].nbytes / t_in / 1e9,
+                 save_s=t_save, save_gb_per_s=file_bytes / t_save / 1e9,
+                 load_s=t_load, load_gb_per_s=file_bytes / t_load / 1e9, file_gb=file_bytes / 1e9)
+            db.close()
+    del big
+
     # device-resident source: the fused normalise + scatter kernel alone
     dev = torch.device("cuda", 0)
     store = DeviceStore(dim, device=0, reserve_rows=1_000_000, bf16_mirror=True)
