@@ -121,6 +121,12 @@ int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const float* vec
 int pvdb_store_download_bf16(pvdb_store_t* s, int64_t row0, int64_t n, uint16_t* out);
 int pvdb_store_upload_bf16(pvdb_store_t* s, int64_t row0, int64_t n, const uint16_t* vecs,
                            const uint32_t* active_bits);
+/* save() of a large store (pico_vdb.py:356): rows [row0, row0+n) are written into the EXISTING file
+ * `path` at byte `file_offset` -- dense fp32 rows, or (as_bf16) the mirror's bit patterns -- device->host
+ * DMA overlapped with pwrite() from pinned buffers.  The caller creates the file with its .npy header
+ * and full size first; ranks of a sharded store write their own row ranges concurrently. */
+int pvdb_store_write_file(pvdb_store_t* s, const char* path, int64_t file_offset, int64_t row0, int64_t n,
+                          int as_bf16);
 /* Copy the active bitmap out: ceil(rows/32) words. */
 int pvdb_store_active_bits(pvdb_store_t* s, uint32_t* out_words);
 /* Compaction: new row i := old row keep_rows[i] (ascending), all n kept rows active, rows := n

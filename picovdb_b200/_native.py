@@ -81,6 +81,7 @@ SIGNATURES = {
     "pvdb_store_upload": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "pvdb_store_download_bf16": (C.c_int, [_P, _I64, _I64, _P]),
     "pvdb_store_upload_bf16": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "pvdb_store_write_file": (C.c_int, [_P, C.c_char_p, _I64, _I64, _I64, C.c_int]),
     "pvdb_store_active_bits": (C.c_int, [_P, _P]),
     "pvdb_store_compact": (C.c_int, [_P, _P, _I64]),
     "pvdb_search": (C.c_int, [_P, _P, _I64, C.c_int, _P, C.c_int, _P, _P]),

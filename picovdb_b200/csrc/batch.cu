@@ -636,9 +636,49 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     unsigned long long stat_local[16] = {};
     STAT_T(e_begin);
 #endif
-    for (int64_t v = v_first; v < n_visits; v += v_step) {
+    // What a visit needs from L2 before it can look at its accumulator -- the query's published
+    // threshold and the mask words of this half (4 words = 128 rows; the active bitmap is allocated up
+    // to capacity, the prefilter only has ceil(rows / 32) words) -- is fetched ONE VISIT AHEAD.  When
+    // the epilogue is the pacing stage (bf16, small dim: 3.1k cycles of MMA per tile) the accumulator
+    // is already full when a warp arrives, so these ~700-cycle round trips sat on the critical path of
+    // every tile (and delayed the first tcgen05.ld behind them).  A threshold that is one visit older
+    // is still a proven lower bound.
+    struct VisitPre {
       int t, qt;
-      if (!decode_unit_visit<CL>(p, v, cta_rank, t, qt)) {
+      bool ok;
+      uint32_t g_pub;
+      uint4 mw;
+    };
+    constexpr int kChunks = kBN / kEpiHalves / 32;  // 32-column chunks per half
+    static_assert(kChunks == 4, "mask words of a half are fetched as one uint4");
+    auto prefetch_visit = [&](int64_t v) -> VisitPre {
+      VisitPre pre;
+      pre.ok = decode_unit_visit<CL>(p, v, cta_rank, pre.t, pre.qt);
+      pre.g_pub = 0u;
+      pre.mw = make_uint4(0u, 0u, 0u, 0u);
+      if (pre.ok) {
+        const int64_t gq = static_cast<int64_t>(pre.qt) * kBM + ql;
+        pre.g_pub = __ldcg(p.shared_thr + (gq < p.nq ? gq : 0));
+        const int64_t row0 = static_cast<int64_t>(p.tile_begin + pre.t) * kBN + half * (kBN / kEpiHalves);
+        pre.mw = __ldg(reinterpret_cast<const uint4*>(p.active + (row0 >> 5)));
+        if (p.prefilter != nullptr) {
+          const int64_t n_pw = (p.n_rows + 31) >> 5;
+          const int64_t w = row0 >> 5;
+          pre.mw.x &= (w + 0 < n_pw) ? __ldg(p.prefilter + w + 0) : 0u;
+          pre.mw.y &= (w + 1 < n_pw) ? __ldg(p.prefilter + w + 1) : 0u;
+          pre.mw.z &= (w + 2 < n_pw) ? __ldg(p.prefilter + w + 2) : 0u;
+          pre.mw.w &= (w + 3 < n_pw) ? __ldg(p.prefilter + w + 3) : 0u;
+        }
+      }
+      return pre;
+    };
+    VisitPre next_pre{};
+    if (v_first < n_visits) next_pre = prefetch_visit(v_first);
+    for (int64_t v = v_first; v < n_visits; v += v_step) {
+      const VisitPre cur = next_pre;
+      if (v + v_step < n_visits) next_pre = prefetch_visit(v + v_step);
+      const int t = cur.t, qt = cur.qt;
+      if (!cur.ok) {
         // padding query tile of an odd count: nothing to select, just recycle the accumulator
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
@@ -667,37 +707,23 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       // serving a query tile warms its threshold up on its own and collects ~37x more candidates.
       const int64_t gq = static_cast<int64_t>(qt) * kBM + ql;
       uint32_t* gthr = p.shared_thr + (gq < p.nq ? gq : 0);
-      // loads whose latency hides behind the wait for the accumulator: published threshold and the
-      // mask words of this half (4 words = 128 rows; the active bitmap is allocated up to capacity,
-      // the prefilter only has ceil(rows / 32) words)
-      const uint32_t g_pub = __ldcg(gthr);
+      const uint32_t g_pub = cur.g_pub;
       const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN + half * (kBN / kEpiHalves);
-      constexpr int kChunks = kBN / kEpiHalves / 32;  // 32-column chunks per half
-      static_assert(kChunks == 4, "mask words of a half are fetched as one uint4");
-      const uint4 aw4 = __ldg(reinterpret_cast<const uint4*>(p.active + (row0 >> 5)));
-      uint32_t mwords[kChunks] = {aw4.x, aw4.y, aw4.z, aw4.w};
-      if (p.prefilter != nullptr) {
-        const int64_t n_pw = (p.n_rows + 31) >> 5;
-#pragma unroll
-        for (int i = 0; i < kChunks; ++i) {
-          const int64_t w = (row0 >> 5) + i;
-          mwords[i] &= (w < n_pw) ? __ldg(p.prefilter + w) : 0u;
-        }
-      }
+      const uint32_t mwords[kChunks] = {cur.mw.x, cur.mw.y, cur.mw.z, cur.mw.w};
       STAT_T(e0);
       mbar_wait(tfull_bar(acc), acc_phase);
       STAT_ADD(1, clock64() - e0);
+      tcgen05_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                              static_cast<uint32_t>(acc * kBN + half * (kBN / kEpiHalves));
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr0, va);  // first chunk on its way before anything else is looked at
       if (gq < p.nq && g_pub > 1u) thr = fmaxf(thr, ordered_to_f32(g_pub - 1u));  // keep scores >= published
       STAT_ADD(9, 1);
 #ifdef PVDB_BATCH_STATS
       const int cnt_before_visit = cnt;
       int pruned_away = 0;
 #endif
-      tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                              static_cast<uint32_t>(acc * kBN + half * (kBN / kEpiHalves));
-      uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr0, va);
       if (p.dump != nullptr) {
         // seed pass: the masked scores themselves are wanted (seed_threshold_kernel selects from them)
         float* drow = p.dump + static_cast<size_t>(gq) * p.dump_ld + (static_cast<size_t>(t) * kBN + half * (kBN / kEpiHalves));

@@ -5,7 +5,11 @@
 //   row fetch / download / raw upload / compaction (pico_vdb.py:945, 356, 233-259, 840-848)
 #include <cuda.h>
 
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -829,6 +833,102 @@ extern "C" int pvdb_store_upload(pvdb_store_t* s, int64_t row0, int64_t n, const
   s->rows = std::max(s->rows, row0 + n);
   PVDB_CUDA(cudaStreamSynchronize(st));
   return PVDB_OK;
+}
+
+// pwrite of one block, split over a few threads (the copy into the page cache is the slow side)
+static int parallel_pwrite(int fd, const void* src, size_t bytes, int64_t offset) {
+  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned want = std::min<unsigned>(4, std::max<unsigned>(1, hw / 2));
+  const size_t min_piece = size_t(4) << 20;
+  const unsigned n = static_cast<unsigned>(std::min<size_t>(want, std::max<size_t>(1, bytes / min_piece)));
+  const size_t piece = ((bytes + n - 1) / n + 4095) & ~size_t(4095);
+  std::vector<int> err(n, 0);
+  auto work = [&](unsigned i) {
+    size_t off = std::min(bytes, piece * i);
+    size_t len = std::min(bytes - off, piece);
+    while (len > 0) {
+      const ssize_t w = pwrite(fd, static_cast<const char*>(src) + off, len, offset + static_cast<int64_t>(off));
+      if (w < 0) {
+        if (errno == EINTR) continue;
+        err[i] = errno;
+        return;
+      }
+      off += static_cast<size_t>(w);
+      len -= static_cast<size_t>(w);
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned i = 1; i < n; ++i) th.emplace_back(work, i);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int e : err)
+    if (e) return fail(PVDB_ERR_INVALID, "write to the vector file failed: %s", strerror(e));
+  return PVDB_OK;
+}
+
+// Rows [row0, row0 + n) straight into an existing file at file_offset (dense fp32 rows, or the bf16
+// mirror's bit patterns): the save() of a large store.  The device->host DMA of block i+1 overlaps the
+// pwrite of block i out of the other pinned buffer; nothing is staged in pageable memory and no page of
+// a mapped file is faulted in (mapping a fresh 6 GB .npy and storing into it ran at 1.9 GB/s).
+extern "C" int pvdb_store_write_file(pvdb_store_t* s, const char* path, int64_t file_offset, int64_t row0, int64_t n,
+                                     int as_bf16) {
+  PVDB_ENTER(s);
+  if (n == 0) return PVDB_OK;
+  if (!path || n < 0 || row0 < 0 || row0 + n > s->rows || file_offset < 0)
+    return fail(PVDB_ERR_INVALID, "write_file: bad arguments (rows [%lld, %lld) of %lld)", (long long)row0,
+                (long long)(row0 + n), (long long)s->rows);
+  if (as_bf16 && !s->bf16.ptr) return fail(PVDB_ERR_UNSUPPORTED, "write_file: this store keeps no bf16 mirror");
+  const int fd = open(path, O_WRONLY);
+  if (fd < 0) return fail(PVDB_ERR_INVALID, "write_file: cannot open %s: %s", path, strerror(errno));
+  cudaStream_t st = s->stream;
+  int rc = s->use_stream(st);
+  const size_t row_bytes = static_cast<size_t>(s->dim) * (as_bf16 ? 2 : 4);
+  const int64_t per = std::max<int64_t>(1, kPipeBytes / static_cast<int64_t>(row_bytes));
+  if (rc == PVDB_OK) rc = s->h_pipe[0].ensure(static_cast<size_t>(std::min(per, n)) * row_bytes);
+  if (rc == PVDB_OK && n > per) rc = s->h_pipe[1].ensure(static_cast<size_t>(std::min(per, n)) * row_bytes);
+  if (rc == PVDB_OK && !as_bf16 && !s->f32.ptr) rc = s->d_in.ensure(static_cast<size_t>(std::min(per, n)) * row_bytes);
+  auto enqueue = [&](void* pinned, int64_t i0, int64_t m) -> int {
+    if (as_bf16) {
+      const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(s->bf16.ptr) + (row0 + i0) * s->ld_bf16;
+      PVDB_CUDA(cudaMemcpy2DAsync(pinned, row_bytes, src, static_cast<size_t>(s->ld_bf16) * 2, row_bytes,
+                                  static_cast<size_t>(m), cudaMemcpyDeviceToHost, st));
+    } else if (s->f32.ptr) {
+      const float* src = static_cast<const float*>(s->f32.ptr) + (row0 + i0) * s->ld_f32;
+      PVDB_CUDA(cudaMemcpy2DAsync(pinned, row_bytes, src, static_cast<size_t>(s->ld_f32) * 4, row_bytes,
+                                  static_cast<size_t>(m), cudaMemcpyDeviceToHost, st));
+    } else {
+      gather_rows_kernel<<<warp_grid(m), 256, 0, st>>>(nullptr, row0 + i0, m, s->dim, nullptr, s->ld_f32,
+                                                       static_cast<const __nv_bfloat16*>(s->bf16.ptr), s->ld_bf16,
+                                                       static_cast<float*>(s->d_in.ptr));
+      PVDB_LAUNCH_CHECK();
+      PVDB_CUDA(cudaMemcpyAsync(pinned, s->d_in.ptr, static_cast<size_t>(m) * row_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    return PVDB_OK;
+  };
+  int b = 0;
+  int64_t prev0 = -1, prev_m = 0;
+  for (int64_t i0 = 0; i0 < n && rc == PVDB_OK; i0 += per, b ^= 1) {
+    const int64_t m = std::min(per, n - i0);
+    rc = enqueue(s->h_pipe[b].ptr, i0, m);
+    if (rc == PVDB_OK && cudaEventRecord(s->pipe_ev[b], st) != cudaSuccess) rc = fail(PVDB_ERR_CUDA, "cudaEventRecord failed");
+    if (rc == PVDB_OK && prev0 >= 0) {
+      if (cudaEventSynchronize(s->pipe_ev[b ^ 1]) != cudaSuccess) rc = fail(PVDB_ERR_CUDA, "cudaEventSynchronize failed");
+      if (rc == PVDB_OK)
+        rc = parallel_pwrite(fd, s->h_pipe[b ^ 1].ptr, static_cast<size_t>(prev_m) * row_bytes,
+                             file_offset + prev0 * static_cast<int64_t>(row_bytes));
+    }
+    prev0 = i0;
+    prev_m = m;
+  }
+  if (rc == PVDB_OK && prev0 >= 0) {
+    if (cudaEventSynchronize(s->pipe_ev[b ^ 1]) != cudaSuccess) rc = fail(PVDB_ERR_CUDA, "cudaEventSynchronize failed");
+    if (rc == PVDB_OK)
+      rc = parallel_pwrite(fd, s->h_pipe[b ^ 1].ptr, static_cast<size_t>(prev_m) * row_bytes,
+                           file_offset + prev0 * static_cast<int64_t>(row_bytes));
+  }
+  cudaStreamSynchronize(st);
+  close(fd);
+  return rc;
 }
 
 // Raw load of bf16 rows (what pvdb_store_download_bf16 wrote) into a bf16-only store.

@@ -630,14 +630,21 @@ class PicoVectorDB:
             out = open_memmap(path, mode="r+")
         lo, hi = eng.owned_rows() if sharded else (0, n)
         lo, hi = max(lo, 0), min(hi, n)
+        if hasattr(eng, "write_file"):
+            # the library streams device -> pinned -> pwrite() into the file (the map above only created
+            # header + size); slots the engine never wrote stay the zeros of the sparse file
+            row_bytes = self.dim * out.dtype.itemsize
+            offset = int(out.offset)
+            del out
+            hi = min(hi, int(eng.rows))
+            if hi > lo:
+                eng.write_file(path, offset + lo * row_bytes, lo, hi - lo, as16)
+            self._engine_barrier()
+            return
         step = max(1, (512 << 20) // (self.dim * out.dtype.itemsize))
-        direct = getattr(eng, "download_into", False)  # DeviceStore: stream straight into the mapped file
         for r0 in range(lo, hi, step):
             r1 = min(hi, r0 + step)
-            have = max(0, min(r1, int(eng.rows)) - r0) if direct else 0
-            if direct and have == r1 - r0:
-                (eng.download_bf16 if as16 else eng.download)(r0, r1 - r0, out=out[r0:r1])
-            elif as16:
+            if as16:
                 out[r0:r1] = eng.download_bf16(r0, r1 - r0)
             else:
                 out[r0:r1] = self._download(r0, r1 - r0)

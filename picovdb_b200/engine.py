@@ -8,6 +8,7 @@ library; this file only marshals pointers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -199,6 +200,11 @@ class DeviceStore:
             raise ValueError(f"upload_bf16 expects (n, {self.dim}) uint16 rows")
         bits = None if active is None else pack_row_mask(active)
         N.check(self._lib.pvdb_store_upload_bf16(self.handle, int(row0), v.shape[0], _ptr(v), _ptr(bits)))
+
+    def write_file(self, path: str, file_offset: int, row0: int, n: int, as_bf16: bool = False) -> None:
+        """Rows [row0, row0 + n) into the existing file at ``file_offset`` (see pvdb_store_write_file)."""
+        N.check(self._lib.pvdb_store_write_file(self.handle, os.fsencode(path), int(file_offset), int(row0), int(n),
+                                                1 if as_bf16 else 0))
 
     def active_mask(self) -> np.ndarray:
         n = self.rows

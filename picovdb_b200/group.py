@@ -195,6 +195,14 @@ class GroupStore:
                 out[a - row0: b - row0] = self.shards[i].download_bf16(a - lo, b - a)
         return out
 
+    def write_file(self, path: str, file_offset: int, row0: int, n: int, as_bf16: bool = False) -> None:
+        row_bytes = self.dim * (2 if as_bf16 else 4)
+        for i in range(self.world):
+            lo, hi = self.shard_bounds(i)
+            a, b = max(row0, lo), min(row0 + n, hi, lo + self.shards[i].rows)
+            if b > a:
+                self.shards[i].write_file(path, file_offset + (a - row0) * row_bytes, a - lo, b - a, as_bf16)
+
     def active_mask(self) -> np.ndarray:
         out = np.zeros(self._rows, dtype=bool)
         for i in range(self.world):

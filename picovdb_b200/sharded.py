@@ -432,6 +432,18 @@ class ShardedStore:
             out[lo - row0: hi - row0] = self.local.download_bf16(lo - self.row0, hi - lo)
         return out
 
+    def write_file(self, path: str, file_offset: int, row0: int, n: int, as_bf16: bool = False) -> None:
+        """This rank's written rows of [row0, row0 + n) into the file (``file_offset`` = where row0 goes)."""
+        lo, hi = max(row0, self.row0), min(row0 + n, self.row1, self.row0 + self.local.rows)
+        if hi > lo and hasattr(self.local, "write_file"):
+            row_bytes = self.dim * (2 if as_bf16 else 4)
+            self.local.write_file(path, file_offset + (lo - row0) * row_bytes, lo - self.row0, hi - lo, as_bf16)
+        elif hi > lo:  # test engines: through a map
+            mm = np.memmap(path, dtype=np.uint16 if as_bf16 else np.float32, mode="r+", offset=file_offset,
+                           shape=(n, self.dim))
+            mm[lo - row0: hi - row0] = (self.local.download_bf16 if as_bf16 else self.local.download)(lo - self.row0, hi - lo)
+            mm.flush()
+
     def compact(self, keep_rows: np.ndarray) -> None:
         """Global compaction: new row j <- old row keep[j] (keep ascending, so keep[j] >= j and moving
         block by block in ascending order never overwrites a row that is still to be read)."""
