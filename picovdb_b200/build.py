@@ -77,6 +77,32 @@ def is_current() -> bool:
         return f.read().strip() == _fingerprint()
 
 
+def build_variant(name: str, extra_flags: list[str]) -> str:
+    """An instrumented / experimental copy of the library next to the product one, e.g.
+    ``build_variant("stats", ["-DPVDB_BATCH_STATS"])`` -> picovdb_b200/_variants/libpicovdb_b200_stats.so
+    (select it with PICOVDB_B200_LIB=...).  Never used by the product path."""
+    nvcc = find_nvcc()
+    out_dir = os.path.join(PKG_DIR, "_variants")
+    obj_dir = os.path.join(out_dir, name)
+    os.makedirs(obj_dir, exist_ok=True)
+    lib = os.path.join(out_dir, f"libpicovdb_b200_{name}.so")
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(os.path.basename(src))[0] + ".o")
+        cmd = [nvcc, *COMPILE_FLAGS, *extra_flags, "-I", INCLUDE, "-c", src, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)}:\n{res.stdout}\n{res.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=max(1, os.cpu_count() or 1)) as ex:
+        objects = list(ex.map(compile_one, _sources()))
+    res = subprocess.run([nvcc, *LINK_FLAGS, "-o", lib, *objects], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc link failed:\n{res.stdout}\n{res.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile what changed, link, return the library path."""
     if not force and is_current():
@@ -121,5 +147,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(path)

@@ -46,6 +46,7 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
     PVDB_CUDA(cudaMemsetAsync(ctrl, 0, 64, st));
     s->partial_gen_inited = s->d_partial.gen;
   }
+  static const bool no_pdl = getenv("PVDB_SCAN_NO_PDL") != nullptr;
   ScanParams p{};
   p.matrix = bf16 ? s->bf16.ptr : s->f32.ptr;
   p.n_rows = s->rows;
@@ -68,6 +69,9 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
       p.out_rows = d_out_rows + q * k + k0;
       p.xv = ExchangeView{};
       if (ex != nullptr) p.xv = ex->next_view();
+      // second and later launches of this call: the previous operation on the stream is a scan whose
+      // inputs were complete before it started (PVDB_SCAN_NO_PDL=1 switches the overlap off)
+      p.pdl = (q > 0 || k0 > 0) && !no_pdl;
       PVDB_TRY(launch_scan(p, bf16, st));
     }
   }

@@ -80,6 +80,7 @@ constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the databa
 // SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
 // C5 batch: 34.9 vs 32.4 ms), so it stays opt-in.
 constexpr bool kPairDefault = false;
+constexpr bool kAltDefault = false;  // alternate-accumulator epilogue (PVDB_BATCH_ALT=1): see the epilogue
 constexpr int kClusterDefault = 2;  // CTAs per cluster sharing a database tile; 4 and 8 work but measured 3 % / 10 % slower
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 ordered u32][cnt: 2 x 32 x 128 u16][touched: 32 B]
@@ -433,7 +434,7 @@ __device__ unsigned long long g_batch_stats[16];
 // is then 16 KB + 16 KB per CTA, so the same 192 KB ring holds 6 stages instead of 4 (deeper
 // pipeline against L2 latency) and each CTA pulls 32 KB instead of 48 KB per K block.  The leader
 // (even) CTA issues the MMAs and owns the full / tmem_empty barriers; commits are multicast.
-template <bool BF16, int NI, int CL, bool PAIR>
+template <bool BF16, int NI, int CL, bool PAIR, bool ALT>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                   const BatchParams p) {
@@ -477,8 +478,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      // one arrival per epilogue warp (of both CTAs for a pair)
-      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * kEpiHalves);
+      // one arrival per epilogue warp that reads the accumulator (of both CTAs for a pair)
+      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * (ALT ? 1 : kEpiHalves));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -611,12 +612,20 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ======================= epilogue: mask + running top-k =======================
+    // Two groups of four warps (one warp per TMEM lane quarter in each).  ALT = false: both groups
+    // work on every accumulator, group g on its 128-column half.  ALT = true: the groups ALTERNATE
+    // accumulators -- group g drains all 256 columns of the visits with index parity g (accumulator g)
+    // -- so every warp streams eight chunks back to back and the per-visit bookkeeping (visit decode,
+    // threshold exchange, barrier hand-over) is paid once per 256 columns instead of once per 128.
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;        // which 128 columns of the accumulator it examines
+    const int grp = (warp - 4) >> 2;         // epilogue group
     const int ql = ew * 32 + lane;           // query (TMEM lane) owned by this thread
-    uint16_t* my_cnt = s_cnt + half * (kMaxQTiles * kBM);
+    constexpr int kCols = ALT ? kBN : kBN / kEpiHalves;   // columns one warp examines per visit
+    constexpr int kChunks = kCols / 32;                   // 32-column chunks per visit and warp
+    const int col0 = ALT ? 0 : grp * kCols;               // first column inside the accumulator
+    uint16_t* my_cnt = s_cnt + grp * (kMaxQTiles * kBM);
     for (int qt = 0; qt < p.q_tiles; ++qt) {
-      if (half == 0) {
+      if (grp == 0) {
         const bool live = (static_cast<int64_t>(qt) * kBM + ql) < p.nq;
         uint32_t t0 = f32_to_ordered(-INFINITY);
         if (live && p.init_thr != nullptr) {
@@ -628,79 +637,80 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
       my_cnt[qt * kBM + ql] = 0;
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // both halves see the initial thresholds
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // both groups see the initial thresholds
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * (kEpiHalves * kBM) * p.pool_cap;
-    int acc = 0;
+    int acc = ALT ? grp : 0;
     uint32_t acc_phase = 0;
 #ifdef PVDB_BATCH_STATS
     unsigned long long stat_local[16] = {};
     STAT_T(e_begin);
 #endif
     // What a visit needs from L2 before it can look at its accumulator -- the query's published
-    // threshold and the mask words of this half (4 words = 128 rows; the active bitmap is allocated up
-    // to capacity, the prefilter only has ceil(rows / 32) words) -- is fetched ONE VISIT AHEAD.  When
-    // the epilogue is the pacing stage (bf16, small dim: 3.1k cycles of MMA per tile) the accumulator
-    // is already full when a warp arrives, so these ~700-cycle round trips sat on the critical path of
-    // every tile (and delayed the first tcgen05.ld behind them).  A threshold that is one visit older
-    // is still a proven lower bound.
+    // threshold and the mask words of its columns (one word per 32-column chunk; the active bitmap is
+    // allocated up to capacity, the prefilter only has ceil(rows / 32) words) -- is fetched ONE VISIT
+    // AHEAD.  When the epilogue is the pacing stage (bf16, small dim: 3.1k cycles of MMA per tile) the
+    // accumulator is already full when a warp arrives, so these ~700-cycle round trips sat on the
+    // critical path of every tile (and delayed the first tcgen05.ld behind them).  A threshold that is
+    // one visit older is still a proven lower bound.  Lane c (< kChunks) holds the mask word of chunk c.
     struct VisitPre {
       int t, qt;
       bool ok;
       uint32_t g_pub;
-      uint4 mw;
+      uint32_t mw;
     };
-    constexpr int kChunks = kBN / kEpiHalves / 32;  // 32-column chunks per half
-    static_assert(kChunks == 4, "mask words of a half are fetched as one uint4");
     auto prefetch_visit = [&](int64_t v) -> VisitPre {
       VisitPre pre;
       pre.ok = decode_unit_visit<CL>(p, v, cta_rank, pre.t, pre.qt);
       pre.g_pub = 0u;
-      pre.mw = make_uint4(0u, 0u, 0u, 0u);
+      pre.mw = 0u;
       if (pre.ok) {
         const int64_t gq = static_cast<int64_t>(pre.qt) * kBM + ql;
         pre.g_pub = __ldcg(p.shared_thr + (gq < p.nq ? gq : 0));
-        const int64_t row0 = static_cast<int64_t>(p.tile_begin + pre.t) * kBN + half * (kBN / kEpiHalves);
-        pre.mw = __ldg(reinterpret_cast<const uint4*>(p.active + (row0 >> 5)));
-        if (p.prefilter != nullptr) {
-          const int64_t n_pw = (p.n_rows + 31) >> 5;
-          const int64_t w = row0 >> 5;
-          pre.mw.x &= (w + 0 < n_pw) ? __ldg(p.prefilter + w + 0) : 0u;
-          pre.mw.y &= (w + 1 < n_pw) ? __ldg(p.prefilter + w + 1) : 0u;
-          pre.mw.z &= (w + 2 < n_pw) ? __ldg(p.prefilter + w + 2) : 0u;
-          pre.mw.w &= (w + 3 < n_pw) ? __ldg(p.prefilter + w + 3) : 0u;
+        const int64_t w = ((static_cast<int64_t>(p.tile_begin + pre.t) * kBN + col0) >> 5) + lane;
+        if (lane < kChunks) {
+          pre.mw = __ldg(p.active + w);
+          if (p.prefilter != nullptr) pre.mw &= (w < ((p.n_rows + 31) >> 5)) ? __ldg(p.prefilter + w) : 0u;
         }
       }
       return pre;
     };
+    const int64_t e_step = ALT ? 2 * v_step : v_step;           // visits between two of this group's
+    const int64_t e_first = v_first + (ALT ? grp * v_step : 0);
     VisitPre next_pre{};
-    if (v_first < n_visits) next_pre = prefetch_visit(v_first);
-    for (int64_t v = v_first; v < n_visits; v += v_step) {
+    if (e_first < n_visits) next_pre = prefetch_visit(e_first);
+    for (int64_t v = e_first; v < n_visits; v += e_step) {
       const VisitPre cur = next_pre;
-      if (v + v_step < n_visits) next_pre = prefetch_visit(v + v_step);
+      if (v + e_step < n_visits) next_pre = prefetch_visit(v + e_step);
       const int t = cur.t, qt = cur.qt;
-      if (!cur.ok) {
-        // padding query tile of an odd count: nothing to select, just recycle the accumulator
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tcgen05_fence_after();
+      auto release_accumulator = [&]() {
+        // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) {
           if (is_leader) mbar_arrive(tempty_bar(acc));
           else mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);
         }
-        if (++acc == 2) {
+        if constexpr (ALT) {
+          acc_phase ^= 1u;           // this group always drains accumulator `grp`
+        } else if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
+      };
+      if (!cur.ok) {
+        // padding query tile of an odd count: nothing to select, just recycle the accumulator
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tcgen05_fence_after();
+        release_accumulator();
         continue;
       }
-      uint64_t* warp_pools = cta_pools + ((static_cast<size_t>(qt) * kEpiHalves + half) * kBM + ew * 32) * p.pool_cap;
-      // The threshold of a query is shared by its two halves (and, below, by all CTAs): whoever
+      uint64_t* warp_pools = cta_pools + ((static_cast<size_t>(qt) * kEpiHalves + grp) * kBM + ew * 32) * p.pool_cap;
+      // The threshold of a query is shared by the two groups (and, below, by all CTAs): whoever
       // holds k_sel candidates proves a lower bound of the final k_sel-th best for everybody.
       const uint32_t thr_in = s_thr[qt * kBM + ql];
       float thr = ordered_to_f32(thr_in);
       int cnt = my_cnt[qt * kBM + ql];
-      if (lane == 0 && warp == 4) s_touched[qt] = 1;
+      if (lane == 0 && ew == 0) s_touched[qt] = 1;   // (the groups may meet different query tiles)
       // Shared threshold: every CTA that holds k_sel candidates for this query publishes its k_sel-th
       // score (atomicMax below).  The global k_sel-th best is >= each of them, so anything strictly
       // below the published maximum can be skipped by everybody; without this each of the ~37 CTAs
@@ -708,14 +718,12 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const int64_t gq = static_cast<int64_t>(qt) * kBM + ql;
       uint32_t* gthr = p.shared_thr + (gq < p.nq ? gq : 0);
       const uint32_t g_pub = cur.g_pub;
-      const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN + half * (kBN / kEpiHalves);
-      const uint32_t mwords[kChunks] = {cur.mw.x, cur.mw.y, cur.mw.z, cur.mw.w};
+      const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN + col0;
       STAT_T(e0);
       mbar_wait(tfull_bar(acc), acc_phase);
       STAT_ADD(1, clock64() - e0);
       tcgen05_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
-                              static_cast<uint32_t>(acc * kBN + half * (kBN / kEpiHalves));
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN + col0);
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr0, va);  // first chunk on its way before anything else is looked at
       if (gq < p.nq && g_pub > 1u) thr = fmaxf(thr, ordered_to_f32(g_pub - 1u));  // keep scores >= published
@@ -726,12 +734,13 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #endif
       if (p.dump != nullptr) {
         // seed pass: the masked scores themselves are wanted (seed_threshold_kernel selects from them)
-        float* drow = p.dump + static_cast<size_t>(gq) * p.dump_ld + (static_cast<size_t>(t) * kBN + half * (kBN / kEpiHalves));
+        float* drow = p.dump + static_cast<size_t>(gq) * p.dump_ld + (static_cast<size_t>(t) * kBN + col0);
 #pragma unroll
         for (int cb = 0; cb < kChunks; ++cb) {
+          const uint32_t mw = __shfl_sync(0xffffffffu, cur.mw, cb);
           tmem_ld_wait(va);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) vb[j] = ((mwords[cb] >> j) & 1u) ? va[j] : 0xff800000u;
+          for (int j = 0; j < 32; ++j) vb[j] = ((mw >> j) & 1u) ? va[j] : 0xff800000u;
           if (cb + 1 < kChunks) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 1) * 32), va);
           uint4* d4 = reinterpret_cast<uint4*>(drow + cb * 32);
 #pragma unroll
@@ -741,14 +750,22 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll 1
       for (int cb = 0; cb < kChunks; cb += 2) {
         // mask words of the two 32-column chunks of this step (warp-uniform)
-        const uint32_t mw0 = cb == 0 ? mwords[0] : mwords[2], mw1 = cb == 0 ? mwords[1] : mwords[3];
+        const uint32_t mw0 = __shfl_sync(0xffffffffu, cur.mw, cb), mw1 = __shfl_sync(0xffffffffu, cur.mw, cb + 1);
         // chunk cb is in flight into `va`; start chunk cb+1 into `vb` before examining `va`
+        STAT_T(w0);
         tmem_ld_wait(va);
+        STAT_ADD(11, clock64() - w0);
         tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 1) * 32), vb);
+        STAT_T(c0);
         if (mw0 != 0u) scan_chunk(va, mw0, thr, warp_pools, lane, cnt, static_cast<uint32_t>(row0) + cb * 32);
+        STAT_ADD(12, clock64() - c0);
+        STAT_T(w1);
         tmem_ld_wait(vb);
+        STAT_ADD(11, clock64() - w1);
         if (cb + 2 < kChunks) tmem_ld_32x32(taddr0 + static_cast<uint32_t>((cb + 2) * 32), va);
+        STAT_T(c1);
         if (mw1 != 0u) scan_chunk(vb, mw1, thr, warp_pools, lane, cnt, static_cast<uint32_t>(row0) + (cb + 1) * 32);
+        STAT_ADD(12, clock64() - c1);
         // pools that could overflow during the next 64 columns are pruned now (warp co-operative)
         unsigned need = __ballot_sync(0xffffffffu, cnt > p.pool_cap - 64);
         if (need) __syncwarp();
@@ -781,18 +798,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         STAT_ADD(4, appended);
       }
 #endif
-      // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (is_leader) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
-      }
-      // The other half may be one visit ahead or behind, so a bound proven here is shared NON-strictly
+      release_accumulator();
+      // The other group may be a visit ahead or behind, so a bound proven here is shared NON-strictly
       // (one ulp lower): a row with exactly the k_sel-th score must not be dropped there, it could
       // have the lower row number and win the tie.
       const uint32_t thr_out = f32_to_ordered(thr) - 1u;
@@ -805,13 +812,15 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int qt = 0; qt < p.q_tiles; ++qt) {
       if (!s_touched[qt] || p.dump != nullptr) continue;
       const size_t u = static_cast<size_t>(blockIdx.x) * p.q_tiles + qt;
-      p.counts[(u * kEpiHalves + half) * kBM + ql] = my_cnt[qt * kBM + ql];
+      p.counts[(u * kEpiHalves + grp) * kBM + ql] = my_cnt[qt * kBM + ql];
       if (warp == 4 && lane == 0) p.touched[u] = 1;
     }
 #ifdef PVDB_BATCH_STATS
     if (lane == 0)
       for (int i = 0; i <= 4; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
     if (lane == 0) atomicAdd(&g_batch_stats[9], stat_local[9]);
+    if (lane == 0) atomicAdd(&g_batch_stats[11], stat_local[11]);
+    if (lane == 0) atomicAdd(&g_batch_stats[12], stat_local[12]);
     if (lane == 0 && warp == 4 && blockIdx.x == 0) atomicAdd(&g_batch_stats[10], 1ull);
 #endif
   }
@@ -1224,20 +1233,26 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
 }
 
 // Kernel variant for (element type, cluster size, pair MMA, pool size).
-template <bool BF16, int CL, bool PAIR>
+template <bool BF16, int CL, bool PAIR, bool ALT>
 static const void* batch_kernel_ptr(int pool_cap) {
-  return pool_cap == 128 ? reinterpret_cast<const void*>(batch_topk_kernel<BF16, 4, CL, PAIR>)
-                         : reinterpret_cast<const void*>(batch_topk_kernel<BF16, 8, CL, PAIR>);
+  return pool_cap == 128 ? reinterpret_cast<const void*>(batch_topk_kernel<BF16, 4, CL, PAIR, ALT>)
+                         : reinterpret_cast<const void*>(batch_topk_kernel<BF16, 8, CL, PAIR, ALT>);
 }
 
-static const void* batch_kernel(bool bf16, int cl, bool pair, int pool_cap) {
-  if (pair) return bf16 ? batch_kernel_ptr<true, 2, true>(pool_cap) : batch_kernel_ptr<false, 2, true>(pool_cap);
+template <bool BF16, bool ALT>
+static const void* batch_kernel_cl(int cl, bool pair, int pool_cap) {
+  if (pair) return batch_kernel_ptr<BF16, 2, true, false>(pool_cap);
   switch (cl) {
-    case 8: return bf16 ? batch_kernel_ptr<true, 8, false>(pool_cap) : batch_kernel_ptr<false, 8, false>(pool_cap);
-    case 4: return bf16 ? batch_kernel_ptr<true, 4, false>(pool_cap) : batch_kernel_ptr<false, 4, false>(pool_cap);
-    case 2: return bf16 ? batch_kernel_ptr<true, 2, false>(pool_cap) : batch_kernel_ptr<false, 2, false>(pool_cap);
-    default: return bf16 ? batch_kernel_ptr<true, 1, false>(pool_cap) : batch_kernel_ptr<false, 1, false>(pool_cap);
+    case 8: return batch_kernel_ptr<BF16, 8, false, ALT>(pool_cap);
+    case 4: return batch_kernel_ptr<BF16, 4, false, ALT>(pool_cap);
+    case 2: return batch_kernel_ptr<BF16, 2, false, ALT>(pool_cap);
+    default: return batch_kernel_ptr<BF16, 1, false, ALT>(pool_cap);
   }
+}
+
+static const void* batch_kernel(bool bf16, int cl, bool pair, int pool_cap, bool alt) {
+  if (bf16) return alt ? batch_kernel_cl<true, true>(cl, pair, pool_cap) : batch_kernel_cl<true, false>(cl, pair, pool_cap);
+  return alt ? batch_kernel_cl<false, true>(cl, pair, pool_cap) : batch_kernel_cl<false, false>(cl, pair, pool_cap);
 }
 
 static void batch_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int cl, int grid, cudaStream_t st) {
@@ -1329,6 +1344,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   // cta_group::2 MMAs (one M=256 instruction per CTA pair); PVDB_BATCH_PAIR=0 keeps the multicast variant
   const char* pair_env = getenv("PVDB_BATCH_PAIR");
   const bool pair_mma = pair_env ? atoi(pair_env) != 0 : kPairDefault;
+  // epilogue groups alternate accumulators (each drains whole tiles) instead of splitting every tile
+  const char* alt_env = getenv("PVDB_BATCH_ALT");
+  const bool alt_epilogue = alt_env ? atoi(alt_env) != 0 : kAltDefault;
   const void* db_ptr = use_bf16 ? s->bf16.ptr : s->f32.ptr;
   const int db_ld = use_bf16 ? s->ld_bf16 : s->ld_f32;
 
@@ -1425,7 +1443,7 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
         if (p.q_tiles >= c && ((p.q_tiles + c - 1) / c) * c * 4 <= p.q_tiles * 5) cl = c;
       const bool pair = pair_mma && cl >= 2;
       if (pair) cl = 2;
-      const void* kern = batch_kernel(use_bf16, cl, pair, p.pool_cap);
+      const void* kern = batch_kernel(use_bf16, cl, pair, p.pool_cap, alt_epilogue && !dump_scores);
       int max_units = 0;
       PVDB_TRY(batch_max_units(kern, cl, &max_units));
       CUtensorMap mdb;  // box = the rows one CTA fetches per K block

@@ -36,6 +36,10 @@ struct ScanParams {
   float* out_scores;         // [k]
   int64_t* out_rows;         // [k]
   int64_t row_base;
+  int pdl;                   // host side: launch with programmatic dependent launch (the previous launch on
+                             // the stream is a scan of the same call: its inputs are complete, only the
+                             // per-block lists / ticket / paging bound are shared -- the kernel waits for
+                             // the previous grid right before it touches those)
   ExchangeView xv;           // xv.world > 0: the last block exchanges its list with the peer GPUs and
                              // merges theirs before writing the result (exchange.cuh); not with paging
 };

@@ -51,6 +51,13 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   const int gi = lane / LPR;
   const int k = p.k;
 
+  // Programmatic dependent launch: let the next scan on the stream start filling SMs as soon as this
+  // grid's blocks retire (its scan phase only reads the matrix), and wait for the PREVIOUS grid only
+  // where this one touches what that one may still be using (below: paging bound, per-block lists).
+  // Both instructions are no-ops in a launch without the attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.upper != nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (p.raw_query != nullptr) {
     // Fused query preparation (picovdb/pico_vdb.py:584-591): every block normalises the raw query
     // itself -- fp32 sum of squares, fp32 norm, IEEE division, zero query -> e0 -- which saves a
@@ -205,6 +212,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   // ---- block merge: warp 0 folds the other warps' lists into its own
   store_list(L, slist + warp * k, k, lane);
   __syncthreads();
+  // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (warp == 0) {
     for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
     store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
@@ -308,7 +317,21 @@ static int launch_scan_inst(const ScanParams& p, cudaStream_t stream) {
   auto kern = scan_topk_kernel<BF16, LPR, CH, SPARSE, S>;
   if (smem > 48 * 1024)
     PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<kNumSMs * kScanBlocksPerSM, kScanThreads, smem, stream>>>(p);
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kNumSMs * kScanBlocksPerSM);
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PVDB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<kNumSMs * kScanBlocksPerSM, kScanThreads, smem, stream>>>(p);
+  }
   PVDB_LAUNCH_CHECK();
   return PVDB_OK;
 }

@@ -16,7 +16,8 @@ from picovdb_b200.engine import DeviceStore  # noqa: E402
 from tools.bench_configs import fill, time_search  # noqa: E402
 
 NAMES = ["epi_loop_cyc", "epi_wait_tfull_cyc", "epi_prune_cyc", "prunes", "appended", "epi_final_prune_cyc",
-         "mma_wait_tempty_cyc", "mma_wait_full_cyc", "mma_total_cyc", "epi_warp_visits", "launches"]
+         "mma_wait_tempty_cyc", "mma_wait_full_cyc", "mma_total_cyc", "epi_warp_visits", "launches",
+         "epi_wait_tmem_ld_cyc", "epi_scan_chunk_cyc"]
 
 
 def main():
@@ -37,11 +38,12 @@ def main():
         fn(buf, 16, 1)
         ms1, _, _ = time_search(st, q, k, prec, iters=1, warm=0)
         fn(buf, 16, 0)
-        v = dict(zip(NAMES, [int(x) for x in buf[:11]]))
+        v = dict(zip(NAMES, [int(x) for x in buf[:13]]))
         launches = max(v["launches"], 1)
         ew = 148 * 8  # epilogue warps per launch (upper bound: idle units count as zero time)
         out = {"config": spec, "ms": ms, "launches_in_sample": launches}
-        for name in ("epi_loop_cyc", "epi_wait_tfull_cyc", "epi_prune_cyc", "epi_final_prune_cyc"):
+        for name in ("epi_loop_cyc", "epi_wait_tfull_cyc", "epi_prune_cyc", "epi_final_prune_cyc",
+                     "epi_wait_tmem_ld_cyc", "epi_scan_chunk_cyc"):
             out[name + "_per_warp"] = v[name] / ew
         out["prunes_per_warp"] = v["prunes"] / ew
         out["appended_per_query_state"] = v["appended"] / (148 * 128)
