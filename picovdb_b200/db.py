@@ -333,6 +333,7 @@ class PicoVectorDB:
         keep_f32: bool = True,
         precision: str = "auto",
         save_dtype: Optional[str] = None,
+        max_rows: Optional[int] = None,
     ) -> None:
         self._rwlock = _RWLock()
         self.dim = int(embedding_dim)
@@ -389,11 +390,17 @@ class PicoVectorDB:
         loading = os.path.exists(_ids_path(storage_file)) and (
             os.path.exists(_vecs_path(storage_file)) or os.path.exists(_vecs16_path(storage_file)))
         factory = type(self)._engine_factory
+        # max_rows: size of the engine's row space WITHOUT the reference's capacity= semantics (no
+        # pre-filled slot lists, no free-slot dealing): rows are appended 0, 1, 2, ... as in a plain DB.
+        # This is how a row-sharded engine (devices=[...] / ShardedPicoVectorDB), whose partition must be
+        # fixed up front, takes a 10^8-row bulk load without 10^8 host-side slot entries.
+        if max_rows is not None and capacity is not None:
+            raise ValueError("give either capacity= (pre-allocated slots, as in the reference) or max_rows=")
         if devices is not None and len(devices) > 1:
             # one process, several GPUs: rows sharded over `devices`, searches merged over NVLink
-            # inside the kernels (group.py); needs the total capacity to lay out the partition
-            if capacity is None:
-                raise ValueError("devices=[...] needs capacity= (the row partition over the GPUs is fixed)")
+            # inside the kernels (group.py); needs the total row count to lay out the partition
+            if capacity is None and max_rows is None:
+                raise ValueError("devices=[...] needs capacity= or max_rows= (the row partition over the GPUs is fixed)")
             from .group import GroupStore
 
             def factory(dim, **kw):  # noqa: E306
@@ -405,7 +412,7 @@ class PicoVectorDB:
         self._engine = factory(
             self.dim,
             device=device,
-            reserve_rows=int(capacity) if capacity else 0,
+            reserve_rows=int(capacity) if capacity else (int(max_rows) if max_rows else 0),
             keep_f32=keep_f32,
             bf16_mirror=bf16_mirror,
             fixed_capacity=capacity is not None and not loading,

