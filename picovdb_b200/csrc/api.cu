@@ -250,13 +250,10 @@ extern "C" int pvdb_search_exchange_dev(pvdb_store_t* s, pvdb_exchange_t* ex, co
   return search_dev_entry(s, ex, d_queries, nq, k, d_prefilter_bits, flags, d_out_scores, d_out_rows, stream);
 }
 
-static int search_host_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* queries, int64_t nq, int k,
-                             const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
-  PVDB_ENTER(s);
-  if (ex != nullptr && ex->device != s->device) return fail(PVDB_ERR_INVALID, "search: exchange and store live on different devices");
-  if (nq < 0 || k < 1 || (nq > 0 && (!queries || !out_scores || !out_rows)))
-    return fail(PVDB_ERR_INVALID, "search: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
-  if (nq == 0) return PVDB_OK;
+// Enqueue one host-buffer search on the store's stream (store mutex held by the caller); the results
+// land in the slot's pinned buffer once `slot.done` has completed.
+static int enqueue_host_search(pvdb_store* s, pvdb_store::IoSlot& slot, pvdb_exchange* ex, const float* queries,
+                               int64_t nq, int k, const uint32_t* prefilter_bits, int flags) {
   cudaStream_t st = s->stream;
   PVDB_TRY(s->use_stream(st));
   const size_t q_bytes = static_cast<size_t>(nq) * s->dim * sizeof(float);
@@ -265,7 +262,7 @@ static int search_host_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* qu
   const size_t out_bytes = n_out * (sizeof(int64_t) + sizeof(float));
   PVDB_TRY(s->d_in.ensure(q_bytes));
   PVDB_TRY(s->d_out.ensure(out_bytes));
-  PVDB_TRY(s->h_pinned.ensure(out_bytes));
+  PVDB_TRY(slot.h_res.ensure(out_bytes));
   PVDB_CUDA(cudaMemcpyAsync(s->d_in.ptr, queries, q_bytes, cudaMemcpyHostToDevice, st));
   const uint32_t* d_pref = nullptr;
   if (prefilter_bits && s->rows > 0) {
@@ -278,15 +275,47 @@ static int search_host_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* qu
   // memory is device-addressable under UVA), which removes the D2H copy from the latency of a
   // single query; large ones go through HBM and one bulk copy.
   const bool zero_copy = out_bytes <= (64u << 10);
-  int64_t* d_rows = static_cast<int64_t*>(zero_copy ? s->h_pinned.ptr : s->d_out.ptr);
+  int64_t* d_rows = static_cast<int64_t*>(zero_copy ? slot.h_res.ptr : s->d_out.ptr);
   float* d_scores = reinterpret_cast<float*>(d_rows + n_out);
   PVDB_TRY(search_device(s, static_cast<const float*>(s->d_in.ptr), nq, k, d_pref, flags, d_scores, d_rows, st, ex));
-  if (!zero_copy) PVDB_CUDA(cudaMemcpyAsync(s->h_pinned.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
-  PVDB_CUDA(cudaStreamSynchronize(st));
-  const int64_t* h_rows = static_cast<const int64_t*>(s->h_pinned.ptr);
-  std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
-  std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
+  if (!zero_copy) PVDB_CUDA(cudaMemcpyAsync(slot.h_res.ptr, s->d_out.ptr, out_bytes, cudaMemcpyDeviceToHost, st));
+  PVDB_CUDA(cudaEventRecord(slot.done, st));
   return PVDB_OK;
+}
+
+static int search_host_entry(pvdb_store_t* s, pvdb_exchange* ex, const float* queries, int64_t nq, int k,
+                             const uint32_t* prefilter_bits, int flags, float* out_scores, int64_t* out_rows) {
+  if (s == nullptr) return fail(PVDB_ERR_INVALID, "null store handle");
+  if (ex != nullptr && ex->device != s->device) return fail(PVDB_ERR_INVALID, "search: exchange and store live on different devices");
+  if (nq < 0 || k < 1 || (nq > 0 && (!queries || !out_scores || !out_rows)))
+    return fail(PVDB_ERR_INVALID, "search: bad arguments (nq=%lld, k=%d)", (long long)nq, k);
+  if (nq == 0) return PVDB_OK;
+  const int slot_id = s->acquire_io_slot();  // ours until the results have been copied out
+  pvdb_store::IoSlot& slot = s->io[slot_id];
+  int rc;
+  {
+    std::lock_guard<std::mutex> guard(s->mu);   // held while enqueueing only
+    cudaError_t e = cudaSetDevice(s->device);
+    rc = e == cudaSuccess ? enqueue_host_search(s, slot, ex, queries, nq, k, prefilter_bits, flags)
+                          : fail(PVDB_ERR_CUDA, "cudaSetDevice failed: %s", cudaGetErrorString(e));
+    // a call that failed half way may have work in flight that still writes into the slot
+    if (rc != PVDB_OK && e == cudaSuccess) (void)cudaStreamSynchronize(s->stream);
+  }
+  if (rc == PVDB_OK) {
+    cudaError_t e = cudaEventSynchronize(slot.done);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      rc = fail(PVDB_ERR_CUDA, "search failed on the device: %s", cudaGetErrorString(e));
+    }
+  }
+  if (rc == PVDB_OK) {
+    const size_t n_out = static_cast<size_t>(nq) * k;
+    const int64_t* h_rows = static_cast<const int64_t*>(slot.h_res.ptr);
+    std::memcpy(out_rows, h_rows, n_out * sizeof(int64_t));
+    std::memcpy(out_scores, h_rows + n_out, n_out * sizeof(float));
+  }
+  s->release_io_slot(slot_id);
+  return rc;
 }
 
 extern "C" int pvdb_search(pvdb_store_t* s, const float* queries, int64_t nq, int k,

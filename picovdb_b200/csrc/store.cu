@@ -363,6 +363,26 @@ static inline int warp_grid(int64_t n_items) {
 using namespace pvdb;
 
 // ---------------------------------------------------------------------------- store methods
+int pvdb_store::acquire_io_slot() {
+  std::unique_lock<std::mutex> lk(io_mu);
+  for (;;) {
+    for (int i = 0; i < kIoSlots; ++i)
+      if (!io[i].busy) {
+        io[i].busy = true;
+        return i;
+      }
+    io_cv.wait(lk);
+  }
+}
+
+void pvdb_store::release_io_slot(int slot) {
+  {
+    std::lock_guard<std::mutex> lk(io_mu);
+    io[slot].busy = false;
+  }
+  io_cv.notify_one();
+}
+
 int pvdb_store::use_stream(cudaStream_t s) {
   // last_stream is always a live stream (it starts as the store's own); nullptr is CUDA's legacy
   // default stream, which is just another stream here.
@@ -440,6 +460,10 @@ extern "C" int pvdb_store_create(pvdb_store_t** out, int device, int dim, int64_
   s->h_pipe[0].pinned_host = s->h_pipe[1].pinned_host = true;
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) e = cudaEventCreateWithFlags(&s->pipe_ev[b], cudaEventDisableTiming);
+  for (pvdb_store::IoSlot& io : s->io) {
+    io.h_res.pinned_host = true;
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&io.done, cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&s->d_err_words), 16);
   if (e == cudaSuccess) e = cudaMemset(s->d_err_words, 0, 16);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->order_event, cudaEventDisableTiming);
@@ -477,6 +501,10 @@ extern "C" int pvdb_store_destroy(pvdb_store_t* s) {
     sc->release();
   for (cudaEvent_t ev : s->pipe_ev)
     if (ev) cudaEventDestroy(ev);
+  for (pvdb_store::IoSlot& io : s->io) {
+    io.h_res.release();
+    if (io.done) cudaEventDestroy(io.done);
+  }
   if (s->d_err_words) cudaFree(s->d_err_words);
   if (s->order_event) cudaEventDestroy(s->order_event);
   if (s->stream) cudaStreamDestroy(s->stream);

@@ -2,6 +2,7 @@
 // `_active_indices` array (picovdb/pico_vdb.py:136,143).
 #pragma once
 
+#include <condition_variable>
 #include <mutex>
 #include <vector>
 
@@ -94,6 +95,24 @@ struct pvdb_store {
   int64_t guard_flagged_last = 0;   // queries of the last search that fell back to the exact scan
   int64_t guard_flagged_total = 0;
   uint64_t partial_gen_inited = 0;  // d_partial.gen whose control words have been zeroed
+
+  // Result slots of the host search entry points.  A search holds the store mutex only while it
+  // ENQUEUES its copies and kernels on the store's stream (stream order keeps the shared device scratch
+  // safe); it then waits for its own event and copies its results out of its own pinned buffer with
+  // the mutex released, so concurrent readers of one store overlap their host-side latency (submit,
+  // wake-up, result copy) with each other's GPU work -- the reference computes outside its lock too
+  // (pico_vdb.py:670-714).
+  static constexpr int kIoSlots = 8;
+  struct IoSlot {
+    pvdb::Scratch h_res;          // pinned: kernels write small results straight into it
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+  };
+  IoSlot io[kIoSlots];
+  std::mutex io_mu;
+  std::condition_variable io_cv;
+  int acquire_io_slot();
+  void release_io_slot(int slot);
 
   // Make `s` the stream the store's data is ordered on (inserts an event edge when it changes).
   int use_stream(cudaStream_t s);

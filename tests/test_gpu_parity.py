@@ -613,3 +613,43 @@ def test_bf16_only_db_saves_and_loads_its_mirror(tmp_path):
     assert os.path.exists(path + ".vecs.npy") and not os.path.exists(path + ".vecs.bf16.npy")
     assert np.load(path + ".vecs.npy").shape == (n, dim)
     ref.close()
+
+
+# ------------------------------------------------------------------ concurrent readers of one store
+def test_concurrent_searches_on_one_store(store_factory):
+    """Eight threads search the same handle at once (the store mutex is held only while a call enqueues
+    its work; every call waits for its own event and owns its own pinned result slot): every thread
+    must get exactly what a sequential call returns, for single queries, filtered queries and batches."""
+    import threading
+
+    dim, n, k = 64, 200_000, 10
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 121), 0)
+    queries = _gauss(96, dim, 122)
+    pf = (np.arange(n) % 5) != 0
+    want_one = [s.search(queries[i:i + 1], k) for i in range(96)]
+    want_pf = [s.search(queries[i:i + 1], k, prefilter=pf) for i in range(0, 96, 8)]
+    want_batch = s.search(queries, k, precision="tf32")
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(3):
+                for i in range(t, 96, 8):
+                    got = s.search(queries[i:i + 1], k)
+                    assert np.array_equal(got[1], want_one[i][1]) and np.array_equal(got[0], want_one[i][0])
+                j = t
+                got = s.search(queries[8 * j:8 * j + 1], k, prefilter=pf)
+                assert np.array_equal(got[1], want_pf[j][1])
+                if t % 4 == 0:
+                    got = s.search(queries, k, precision="tf32")
+                    assert np.array_equal(got[1], want_batch[1]) and np.array_equal(got[0], want_batch[0])
+        except Exception as exc:  # noqa: BLE001
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors[:3]

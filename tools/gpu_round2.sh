@@ -21,7 +21,7 @@ for st in $STAGES; do
       cat gpurun_out/gemm_peaks.json ;;
     ncu_list)
       timeout 600 $SHORT > gpurun_out/plain_short.log 2>&1 &&
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv \
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan_topk|batch_topk|finalize_batch|seed_threshold|prepare_queries|merge_topk|exchange_merge|fill_empty" -c 3000 --csv \
         --log-file gpurun_out/launches.csv $SHORT > gpurun_out/ncu_list.log 2>&1
       echo "ncu_list rc=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_scan)
