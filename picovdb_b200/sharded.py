@@ -151,6 +151,14 @@ class ShardedSearch:
         b = self._buffers(nq, k, d_queries.device)
         stream = torch.cuda.current_stream().cuda_stream
         n_out = nq * k
+        if self.world == 1:
+            # nothing to merge: the shard's result IS the result (rows already carry row_base)
+            self.local.search_dev(
+                d_queries.data_ptr(), nq, k, b["scores"].data_ptr(), b["rows"].data_ptr(),
+                d_prefilter=d_prefilter.data_ptr() if d_prefilter is not None else 0,
+                precision=precision, normalized=normalized, stream=stream, scan_only=scan_only,
+            )
+            return b["scores"], b["rows"]
         ex = self._exchange(nq, k)
         if ex is not None:
             # fused: the kernels exchange the lists over peer memory and write the merged result
