@@ -514,11 +514,17 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
+#ifdef PVDB_BATCH_STATS
+      unsigned long long stat_local[16] = {};
+      STAT_T(p_begin);
+#endif
       for (int64_t v = v_first; v < n_visits; v += v_step) {
         int t, qt;
         decode_unit_visit<CL>(p, v, cta_rank, t, qt);  // a padding query tile loads zeros (out of bounds)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
+          STAT_T(p0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          STAT_ADD(13, clock64() - p0);
           const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint32_t b_dst = a_dst + kStageABytes;
           if constexpr (PAIR) {
@@ -551,6 +557,11 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           }
         }
       }
+#ifdef PVDB_BATCH_STATS
+      STAT_ADD(14, clock64() - p_begin);
+      atomicAdd(&g_batch_stats[13], stat_local[13]);
+      atomicAdd(&g_batch_stats[14], stat_local[14]);
+#endif
     }
   } else if (warp == 1) {
     // ======================= MMA issuer =======================

@@ -17,7 +17,7 @@ from tools.bench_configs import fill, time_search  # noqa: E402
 
 NAMES = ["epi_loop_cyc", "epi_wait_tfull_cyc", "epi_prune_cyc", "prunes", "appended", "epi_final_prune_cyc",
          "mma_wait_tempty_cyc", "mma_wait_full_cyc", "mma_total_cyc", "epi_warp_visits", "launches",
-         "epi_wait_tmem_ld_cyc", "epi_scan_chunk_cyc"]
+         "epi_wait_tmem_ld_cyc", "epi_scan_chunk_cyc", "tma_wait_empty_cyc", "tma_total_cyc"]
 
 
 def main():
@@ -38,7 +38,7 @@ def main():
         fn(buf, 16, 1)
         ms1, _, _ = time_search(st, q, k, prec, iters=1, warm=0)
         fn(buf, 16, 0)
-        v = dict(zip(NAMES, [int(x) for x in buf[:13]]))
+        v = dict(zip(NAMES, [int(x) for x in buf[:15]]))
         launches = max(v["launches"], 1)
         ew = 148 * 8  # epilogue warps per launch (upper bound: idle units count as zero time)
         out = {"config": spec, "ms": ms, "launches_in_sample": launches}
@@ -48,7 +48,7 @@ def main():
         out["prunes_per_warp"] = v["prunes"] / ew
         out["appended_per_query_state"] = v["appended"] / (148 * 128)
         out["visits_per_warp"] = v["epi_warp_visits"] / ew
-        for name in ("mma_wait_tempty_cyc", "mma_wait_full_cyc", "mma_total_cyc"):
+        for name in ("mma_wait_tempty_cyc", "mma_wait_full_cyc", "mma_total_cyc", "tma_wait_empty_cyc", "tma_total_cyc"):
             out[name + "_per_cta"] = v[name] / 148
         if v["prunes"]:
             out["cyc_per_prune"] = v["epi_prune_cyc"] / v["prunes"]
