@@ -229,6 +229,23 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// One lane of a CONVERGED warp.  The TMA and MMA warps run their loops with all 32 lanes and let the elected
+// lane issue: operands that are warp-uniform then stay in uniform registers and UTMALDG / UTCHMMA are issued
+// back to back.  Issued from a divergent `if (lane == 0)` branch instead, every tcgen05.mma became an
+// ELECT + 5 x R2UR.BROADCAST + branch "waterfall" loop in SASS, which a micro-benchmark
+// (tools/micro/tmem_ld_mma_bench.cu) timed at 168 cycles per instruction whatever its N -- slower than the
+// 128 cycles a 128 x 256 x 16 MMA needs, i.e. the tensor pipe was paced by instruction issue.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -454,7 +471,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   uint16_t* s_cnt = reinterpret_cast<uint16_t*>(s_thr + kMaxQTiles * kBM);            // [half][q_tiles][128]
   uint8_t* s_touched = reinterpret_cast<uint8_t*>(s_cnt + kEpiHalves * kMaxQTiles * kBM);  // [q_tiles]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
   uint32_t cta_rank = 0;
   if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
@@ -501,16 +518,19 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if constexpr (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone signals them
   else __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * ((p.q_tiles + CL - 1) / CL);
   const int64_t v_first = unit_id < v_step ? unit_id : n_visits;  // surplus units of a pinned schedule idle
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
+    // ======================= TMA producer (all lanes loop, one elected lane issues) =======================
+    {
+      if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_db)) : "memory");
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       constexpr int kElemsPerStage = BF16 ? 64 : 32;
@@ -527,30 +547,37 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           STAT_ADD(13, clock64() - p0);
           const uint32_t a_dst = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint32_t b_dst = a_dst + kStageABytes;
+          const bool issuer = elect_one();
           if constexpr (PAIR) {
             // both CTAs load their own query slice and their half of the tile's rows into their own
             // shared memory; all bytes are counted on the LEADER's full barrier
             const uint32_t lbar = full_bar(stage) & kPeerBitMask;
-            if (is_leader) mbar_expect_tx(full_bar(stage), 2 * kStageAll);
-            tma_load_2d_pair(a_dst, &map_q, lbar, kb * kElemsPerStage, qt * kBM);
-            tma_load_2d_pair(b_dst, &map_db, lbar, kb * kElemsPerStage,
-                             (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * (kBN / 2));
+            if (issuer) {
+              if (is_leader) mbar_expect_tx(full_bar(stage), 2 * kStageAll);
+              tma_load_2d_pair(a_dst, &map_q, lbar, kb * kElemsPerStage, qt * kBM);
+              tma_load_2d_pair(b_dst, &map_db, lbar, kb * kElemsPerStage,
+                               (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * (kBN / 2));
+            }
+            __syncwarp();
             if (++stage == NS) {
               stage = 0;
               phase ^= 1u;
             }
             continue;
           }
-          mbar_expect_tx(full_bar(stage), kStageAll);
-          tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
-          if constexpr (CL == 1) {
-            tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
-          } else {
-            // this CTA fetches its 1/CL share of the tile's rows and multicasts it to the cluster
-            constexpr int kShareRows = kBN / CL;
-            tma_load_2d_mc(b_dst + cta_rank * (kStageBBytes / CL), &map_db, full_bar(stage), kb * kElemsPerStage,
-                           (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * kShareRows, kClusterMask);
+          if (issuer) {
+            mbar_expect_tx(full_bar(stage), kStageAll);
+            tma_load_2d(a_dst, &map_q, full_bar(stage), kb * kElemsPerStage, qt * kBM);
+            if constexpr (CL == 1) {
+              tma_load_2d(b_dst, &map_db, full_bar(stage), kb * kElemsPerStage, (p.tile_begin + t) * kBN);
+            } else {
+              // this CTA fetches its 1/CL share of the tile's rows and multicasts it to the cluster
+              constexpr int kShareRows = kBN / CL;
+              tma_load_2d_mc(b_dst + cta_rank * (kStageBBytes / CL), &map_db, full_bar(stage), kb * kElemsPerStage,
+                             (p.tile_begin + t) * kBN + static_cast<int>(cta_rank) * kShareRows, kClusterMask);
+            }
           }
+          __syncwarp();
           if (++stage == NS) {
             stage = 0;
             phase ^= 1u;
@@ -559,13 +586,15 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
 #ifdef PVDB_BATCH_STATS
       STAT_ADD(14, clock64() - p_begin);
-      atomicAdd(&g_batch_stats[13], stat_local[13]);
-      atomicAdd(&g_batch_stats[14], stat_local[14]);
+      if (lane == 0) {
+        atomicAdd(&g_batch_stats[13], stat_local[13]);
+        atomicAdd(&g_batch_stats[14], stat_local[14]);
+      }
 #endif
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0 && is_leader) {
+    // ======================= MMA issuer (all lanes loop, one elected lane issues) =======================
+    if (is_leader) {
       constexpr uint32_t idesc = make_idesc(BF16, PAIR ? 2 * kBM : kBM);
       int stage = 0;
       uint32_t phase = 0;
@@ -589,28 +618,34 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           const uint32_t a_addr = smem_u32(stage_base + static_cast<size_t>(stage) * kStageAll);
           const uint64_t da = make_smem_desc(a_addr);
           const uint64_t db = make_smem_desc(a_addr + kStageABytes);
+          const bool last_kb = kb + 1 == p.k_blocks;
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < kKBytes / 32; ++j) {
-            // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
-            if constexpr (PAIR)
-              umma_pair<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
-                              (kb | j) != 0 ? 1u : 0u);
-            else
-              umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
-                         (kb | j) != 0 ? 1u : 0u);
+            for (int j = 0; j < kKBytes / 32; ++j) {
+              // advance 32 bytes of K inside the swizzle atom: +2 in the (addr >> 4) field
+              if constexpr (PAIR)
+                umma_pair<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                                (kb | j) != 0 ? 1u : 0u);
+              else
+                umma<BF16>(tmem_d, da + static_cast<uint64_t>(2 * j), db + static_cast<uint64_t>(2 * j), idesc,
+                           (kb | j) != 0 ? 1u : 0u);
+            }
+            // ring slot reusable once these MMAs retire (in every CTA the multicast writes to)
+            if constexpr (PAIR) tcgen05_commit_pair(empty_bar(stage), kClusterMask);
+            else if constexpr (CL == 1) tcgen05_commit(empty_bar(stage));
+            else tcgen05_commit_mc(empty_bar(stage), kClusterMask);
+            if (last_kb) {
+              // accumulator complete (in both CTAs' tensor memory for a pair)
+              if constexpr (PAIR) tcgen05_commit_pair(tfull_bar(acc), kClusterMask);
+              else tcgen05_commit(tfull_bar(acc));
+            }
           }
-          // ring slot reusable once these MMAs retire (in every CTA the multicast writes to)
-          if constexpr (PAIR) tcgen05_commit_pair(empty_bar(stage), kClusterMask);
-          else if constexpr (CL == 1) tcgen05_commit(empty_bar(stage));
-          else tcgen05_commit_mc(empty_bar(stage), kClusterMask);
+          __syncwarp();
           if (++stage == NS) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        // accumulator complete (in both CTAs' tensor memory for a pair)
-        if constexpr (PAIR) tcgen05_commit_pair(tfull_bar(acc), kClusterMask);
-        else tcgen05_commit(tfull_bar(acc));
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
@@ -618,7 +653,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
 #ifdef PVDB_BATCH_STATS
       STAT_ADD(8, clock64() - m_begin);
-      for (int i = 6; i <= 8; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
+      if (lane == 0)
+        for (int i = 6; i <= 8; ++i) atomicAdd(&g_batch_stats[i], stat_local[i]);
 #endif
     }
   } else if (warp >= 4) {
