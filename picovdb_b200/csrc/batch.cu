@@ -80,9 +80,9 @@ constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the databa
 // SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
 // C5 batch: 34.9 vs 32.4 ms), so it stays opt-in.
 constexpr bool kPairDefault = false;
-constexpr bool kAltDefault = false;  // alternate-accumulator epilogue (PVDB_BATCH_ALT=1): see the epilogue
 constexpr int kClusterDefault = 2;  // CTAs per cluster sharing a database tile; 4 and 8 work but measured 3 % / 10 % slower
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
+constexpr int kMaxTileBlock = 8;    // consecutive database tiles a unit gives to ONE query tile (group) -- see VisitSeq
 // shared memory: [ring][barriers + tmem slot (256 B)][thr: 32 x 128 ordered u32][cnt: 2 x 32 x 128 u16][touched: 32 B]
 constexpr size_t kRingBytes = static_cast<size_t>(kStages) * kStageBytes;
 constexpr size_t kStateBytes =
@@ -105,35 +105,64 @@ struct BatchParams {
   uint8_t* touched;      // [grid][q_tiles]: CTA b met query tile qt (zeroed before the launch)
   uint32_t* shared_thr;  // [nq] ordered-int image of the best published k_sel-th score (zeroed)
   int tile_begin;        // first database tile of this launch (n_tiles counts from here)
-  int visit_stride;      // 0: units stride by their count (every unit meets many query tiles);
-                         // else a multiple of the query-tile(-pair) count: unit u keeps ONE query tile
-                         // and units >= visit_stride stay idle (cheap cold start for the sample pass)
+  int tile_block;        // R: database tiles per work item (VisitSeq)
+  int visit_stride;      // 0: units stride over the work items by their count (every unit meets many
+                         // query tiles); else a multiple of the query-tile(-pair) count: unit u keeps ONE
+                         // query tile and units >= visit_stride stay idle (cheap cold start, sample pass)
   const float* init_thr; // optional [nq]: a proven lower bound of each query's k_sel-th best score
   float* dump;           // seed pass only: [q_tiles * 128][dump_ld] masked tensor-core scores are written
   int dump_ld;           //   here (column = row - tile_begin * 256) instead of being selected
 };
 
-// Visit numbering is tile-major: v = t * q_tiles + qt.
-__device__ __forceinline__ void decode_visit(const BatchParams& p, int64_t v, int& t, int& qt) {
-  t = static_cast<int>(v / p.q_tiles);
-  qt = static_cast<int>(v - static_cast<int64_t>(t) * p.q_tiles);
-}
-
-// Cluster variant (CL = 2): the two CTAs of a cluster always work on the same database tile and on
-// two consecutive query tiles, so the tile's K slices can be fetched once and multicast to both.
-// A cluster-visit is (t, query-tile pair); returns false for the padding query tile of an odd count.
+// Work items and visits.  A "visit" is (database tile t, query tile qt).  A WORK ITEM is a block of R
+// consecutive database tiles for one query-tile group (one query tile; with clusters of CL CTAs: CL
+// consecutive query tiles, CTA c of the cluster taking the c-th): item = tile_block * n_groups + group,
+// i.e. items are numbered tile-block-major, and unit u takes items u, u + step, u + 2 step, ...  At any
+// moment the units therefore work inside a window of a few tile blocks (each database tile comes from HBM
+// once and is served to the other query tiles from L2), while inside an item the query tile does not change:
+// the epilogue keeps its thresholds, counters and pool pointers in registers for R visits instead of going
+// through shared memory and a 64-bit division per visit (R = 1 is the round-1 visit order).  The TMA, MMA
+// and epilogue warps all walk the same sequence with this generator; nothing in it divides after start().
 template <int CL>
-__device__ __forceinline__ bool decode_unit_visit(const BatchParams& p, int64_t v, uint32_t cta_rank, int& t, int& qt) {
-  if constexpr (CL == 1) {
-    decode_visit(p, v, t, qt);
-    return true;
-  } else {
-    const int n_qp = (p.q_tiles + CL - 1) / CL;
-    t = static_cast<int>(v / n_qp);
-    qt = static_cast<int>(v - static_cast<int64_t>(t) * n_qp) * CL + static_cast<int>(cta_rank);
-    return qt < p.q_tiles;
+struct VisitSeq {
+  int n_groups, n_tiles, R;
+  int step_tb, step_g;   // item step split into (tile blocks, groups)
+  int64_t item, n_items, step;
+  int tb, g;             // current item
+  int r, nr;             // visit inside the item, visits in the item
+  __device__ __forceinline__ void start(const BatchParams& p, int64_t first_item, int64_t item_step) {
+    n_groups = (p.q_tiles + CL - 1) / CL;
+    n_tiles = p.n_tiles;
+    R = p.tile_block;
+    const int n_tb = (n_tiles + R - 1) / R;
+    n_items = static_cast<int64_t>(n_tb) * n_groups;
+    step = item_step;
+    step_tb = static_cast<int>(item_step / n_groups);
+    step_g = static_cast<int>(item_step - static_cast<int64_t>(step_tb) * n_groups);
+    item = first_item < n_items ? first_item : n_items;
+    tb = static_cast<int>(item / n_groups);
+    g = static_cast<int>(item - static_cast<int64_t>(tb) * n_groups);
+    r = 0;
+    nr = min(R, n_tiles - tb * R);
   }
-}
+  __device__ __forceinline__ bool done() const { return item >= n_items; }
+  __device__ __forceinline__ int t() const { return tb * R + r; }
+  __device__ __forceinline__ int qt(uint32_t cta_rank) const { return g * CL + static_cast<int>(cta_rank); }
+  __device__ __forceinline__ bool first_in_item() const { return r == 0; }
+  __device__ __forceinline__ bool last_in_item() const { return r + 1 == nr; }
+  __device__ __forceinline__ void next() {
+    if (++r < nr) return;
+    item += step;
+    tb += step_tb;
+    g += step_g;
+    if (g >= n_groups) {
+      g -= n_groups;
+      ++tb;
+    }
+    r = 0;
+    nr = min(R, n_tiles - tb * R);
+  }
+};
 
 // ---------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -451,13 +480,13 @@ __device__ unsigned long long g_batch_stats[16];
 // is then 16 KB + 16 KB per CTA, so the same 192 KB ring holds 6 stages instead of 4 (deeper
 // pipeline against L2 latency) and each CTA pulls 32 KB instead of 48 KB per K block.  The leader
 // (even) CTA issues the MMAs and owns the full / tmem_empty barriers; commits are multicast.
-template <bool BF16, int NI, int CL, bool PAIR, bool ALT>
+template <bool BF16, int NI, int CL, bool PAIR>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db,
                   const BatchParams p) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* stage_base = smem;
   static_assert(!PAIR || CL == 2, "a CTA pair is a cluster of two");
   constexpr int NS = PAIR ? 6 : kStages;                                        // ring stages
@@ -477,7 +506,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   if constexpr (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   const int unit_id = static_cast<int>(blockIdx.x) / CL;   // cluster index (== CTA index when CL == 1)
   const int n_units = static_cast<int>(gridDim.x) / CL;
-  const int64_t v_step = p.visit_stride > 0 ? p.visit_stride : n_units;
+  const int64_t i_step = p.visit_stride > 0 ? p.visit_stride : n_units;   // work items between two of this unit's
   constexpr uint16_t kClusterMask = static_cast<uint16_t>((1u << CL) - 1u);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -496,7 +525,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       // one arrival per epilogue warp that reads the accumulator (of both CTAs for a pair)
-      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * (ALT ? 1 : kEpiHalves));
+      mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * 4 * kEpiHalves);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -520,8 +549,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
   tcgen05_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  const int64_t n_visits = static_cast<int64_t>(p.n_tiles) * ((p.q_tiles + CL - 1) / CL);
-  const int64_t v_first = unit_id < v_step ? unit_id : n_visits;  // surplus units of a pinned schedule idle
+  // surplus units of a pinned schedule idle (start() clamps a first item beyond the end to "done")
+  const int64_t i_first = unit_id < i_step ? unit_id : (int64_t(1) << 60);
 
   if (warp == 0) {
     // ======================= TMA producer (all lanes loop, one elected lane issues) =======================
@@ -538,9 +567,9 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       unsigned long long stat_local[16] = {};
       STAT_T(p_begin);
 #endif
-      for (int64_t v = v_first; v < n_visits; v += v_step) {
-        int t, qt;
-        decode_unit_visit<CL>(p, v, cta_rank, t, qt);  // a padding query tile loads zeros (out of bounds)
+      VisitSeq<CL> seq;
+      for (seq.start(p, i_first, i_step); !seq.done(); seq.next()) {
+        const int t = seq.t(), qt = seq.qt(cta_rank);  // a padding query tile loads zeros (out of bounds)
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           STAT_T(p0);
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -604,7 +633,8 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       unsigned long long stat_local[16] = {};
       STAT_T(m_begin);
 #endif
-      for (int64_t v = v_first; v < n_visits; v += v_step) {
+      VisitSeq<CL> seq;
+      for (seq.start(p, i_first, i_step); !seq.done(); seq.next()) {
         STAT_T(m0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
         STAT_ADD(6, clock64() - m0);
@@ -659,17 +689,14 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
   } else if (warp >= 4) {
     // ======================= epilogue: mask + running top-k =======================
-    // Two groups of four warps (one warp per TMEM lane quarter in each).  ALT = false: both groups
-    // work on every accumulator, group g on its 128-column half.  ALT = true: the groups ALTERNATE
-    // accumulators -- group g drains all 256 columns of the visits with index parity g (accumulator g)
-    // -- so every warp streams eight chunks back to back and the per-visit bookkeeping (visit decode,
-    // threshold exchange, barrier hand-over) is paid once per 256 columns instead of once per 128.
+    // Two groups of four warps (one warp per TMEM lane quarter in each); group g works on its 128-column
+    // half of every accumulator.
     const int ew = warp & 3;                 // the TMEM lane quarter this warp may read
     const int grp = (warp - 4) >> 2;         // epilogue group
     const int ql = ew * 32 + lane;           // query (TMEM lane) owned by this thread
-    constexpr int kCols = ALT ? kBN : kBN / kEpiHalves;   // columns one warp examines per visit
-    constexpr int kChunks = kCols / 32;                   // 32-column chunks per visit and warp
-    const int col0 = ALT ? 0 : grp * kCols;               // first column inside the accumulator
+    constexpr int kCols = kBN / kEpiHalves;  // columns one warp examines per visit
+    constexpr int kChunks = kCols / 32;      // 32-column chunks per visit and warp
+    const int col0 = grp * kCols;            // first column inside the accumulator
     uint16_t* my_cnt = s_cnt + grp * (kMaxQTiles * kBM);
     for (int qt = 0; qt < p.q_tiles; ++qt) {
       if (grp == 0) {
@@ -686,49 +713,44 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // both groups see the initial thresholds
     uint64_t* cta_pools = p.pools + static_cast<size_t>(blockIdx.x) * p.q_tiles * (kEpiHalves * kBM) * p.pool_cap;
-    int acc = ALT ? grp : 0;
+    int acc = 0;
     uint32_t acc_phase = 0;
 #ifdef PVDB_BATCH_STATS
     unsigned long long stat_local[16] = {};
     STAT_T(e_begin);
 #endif
-    // What a visit needs from L2 before it can look at its accumulator -- the query's published
-    // threshold and the mask words of its columns (one word per 32-column chunk; the active bitmap is
-    // allocated up to capacity, the prefilter only has ceil(rows / 32) words) -- is fetched ONE VISIT
-    // AHEAD.  When the epilogue is the pacing stage (bf16, small dim: 3.1k cycles of MMA per tile) the
-    // accumulator is already full when a warp arrives, so these ~700-cycle round trips sat on the
-    // critical path of every tile (and delayed the first tcgen05.ld behind them).  A threshold that is
-    // one visit older is still a proven lower bound.  Lane c (< kChunks) holds the mask word of chunk c.
-    struct VisitPre {
-      int t, qt;
-      bool ok;
-      uint32_t g_pub;
-      uint32_t mw;
-    };
-    auto prefetch_visit = [&](int64_t v) -> VisitPre {
-      VisitPre pre;
-      pre.ok = decode_unit_visit<CL>(p, v, cta_rank, pre.t, pre.qt);
-      pre.g_pub = 0u;
-      pre.mw = 0u;
-      if (pre.ok) {
-        const int64_t gq = static_cast<int64_t>(pre.qt) * kBM + ql;
-        pre.g_pub = __ldcg(p.shared_thr + (gq < p.nq ? gq : 0));
-        const int64_t w = ((static_cast<int64_t>(p.tile_begin + pre.t) * kBN + col0) >> 5) + lane;
-        if (lane < kChunks) {
-          pre.mw = __ldg(p.active + w);
-          if (p.prefilter != nullptr) pre.mw &= (w < ((p.n_rows + 31) >> 5)) ? __ldg(p.prefilter + w) : 0u;
-        }
+    // The mask words of a visit's columns (one word per 32-column chunk; lane c < kChunks holds the word of
+    // chunk c; the active bitmap is allocated up to capacity, the prefilter only has ceil(rows / 32) words)
+    // are fetched ONE VISIT AHEAD: when the epilogue is the pacing stage the accumulator is already full
+    // when a warp arrives, and a ~700-cycle L2 round trip would sit on the critical path of every tile.
+    auto load_mask = [&](int t) -> uint32_t {
+      uint32_t mw = 0u;
+      if (lane < kChunks) {
+        const int64_t w = ((static_cast<int64_t>(p.tile_begin + t) * kBN + col0) >> 5) + lane;
+        mw = __ldg(p.active + w);
+        if (p.prefilter != nullptr) mw &= (w < ((p.n_rows + 31) >> 5)) ? __ldg(p.prefilter + w) : 0u;
       }
-      return pre;
+      return mw;
     };
-    const int64_t e_step = ALT ? 2 * v_step : v_step;           // visits between two of this group's
-    const int64_t e_first = v_first + (ALT ? grp * v_step : 0);
-    VisitPre next_pre{};
-    if (e_first < n_visits) next_pre = prefetch_visit(e_first);
-    for (int64_t v = e_first; v < n_visits; v += e_step) {
-      const VisitPre cur = next_pre;
-      if (v + e_step < n_visits) next_pre = prefetch_visit(v + e_step);
-      const int t = cur.t, qt = cur.qt;
+    VisitSeq<CL> seq;
+    seq.start(p, i_first, i_step);
+    uint32_t mw_next = seq.done() ? 0u : load_mask(seq.t());
+    // state of the work item (one query tile for up to R visits), in registers
+    bool ok = false;              // not a padding query tile
+    int qt = 0, sidx = 0;         // query tile; index of this thread's query in s_thr / my_cnt
+    int64_t gq = 0;
+    uint32_t* gthr = p.shared_thr;
+    uint32_t thr_in = 0u, g_pub = 0u;
+    float thr = -INFINITY;
+    int cnt = 0;
+    uint64_t* warp_pools = cta_pools;
+    while (!seq.done()) {
+      const int t = seq.t();
+      const bool first = seq.first_in_item(), last = seq.last_in_item();
+      const int item_qt = seq.qt(cta_rank);
+      const uint32_t cur_mw = mw_next;
+      seq.next();
+      if (!seq.done()) mw_next = load_mask(seq.t());
       auto release_accumulator = [&]() {
         // all of this warp's TMEM reads of the accumulator are done: hand it back to the MMA warp
         tcgen05_fence_before();
@@ -737,34 +759,46 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
           if (is_leader) mbar_arrive(tempty_bar(acc));
           else mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);
         }
-        if constexpr (ALT) {
-          acc_phase ^= 1u;           // this group always drains accumulator `grp`
-        } else if (++acc == 2) {
+        if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1u;
         }
       };
-      if (!cur.ok) {
+      if (first) {
+        // ---- a new work item: load the query tile's state
+        qt = item_qt;
+        ok = qt < p.q_tiles;
+        if (ok) {
+          sidx = qt * kBM + ql;
+          gq = static_cast<int64_t>(qt) * kBM + ql;
+          gthr = p.shared_thr + (gq < p.nq ? gq : 0);
+          // Shared threshold: every CTA that holds k_sel candidates for a query publishes its k_sel-th
+          // score (atomicMax below).  The global k_sel-th best is >= each of them, so anything strictly
+          // below the published maximum can be skipped by everybody; without this each of the ~37 CTAs
+          // serving a query tile warms its threshold up on its own and collects ~37x more candidates.
+          // The load is consumed one visit later (or at the item's end): its L2 round trip hides behind
+          // the first tile.
+          g_pub = __ldcg(gthr);
+          // The threshold of a query is shared by the two groups through shared memory: whoever holds
+          // k_sel candidates proves a lower bound of the final k_sel-th best for everybody.
+          thr_in = s_thr[sidx];
+          thr = ordered_to_f32(thr_in);
+          cnt = my_cnt[sidx];
+          warp_pools = cta_pools + ((static_cast<size_t>(qt) * kEpiHalves + grp) * kBM + ew * 32) * p.pool_cap;
+          if (lane == 0 && ew == 0) s_touched[qt] = 1;   // (the groups may meet different query tiles)
+        }
+      } else if (ok) {
+        // later visits of the item: the other group's bound, and (once it has arrived) the published one
+        thr = fmaxf(thr, ordered_to_f32(s_thr[sidx]));
+        if (gq < p.nq && g_pub > 1u) thr = fmaxf(thr, ordered_to_f32(g_pub - 1u));  // keep scores >= published
+      }
+      if (!ok) {
         // padding query tile of an odd count: nothing to select, just recycle the accumulator
         mbar_wait(tfull_bar(acc), acc_phase);
         tcgen05_fence_after();
         release_accumulator();
         continue;
       }
-      uint64_t* warp_pools = cta_pools + ((static_cast<size_t>(qt) * kEpiHalves + grp) * kBM + ew * 32) * p.pool_cap;
-      // The threshold of a query is shared by the two groups (and, below, by all CTAs): whoever
-      // holds k_sel candidates proves a lower bound of the final k_sel-th best for everybody.
-      const uint32_t thr_in = s_thr[qt * kBM + ql];
-      float thr = ordered_to_f32(thr_in);
-      int cnt = my_cnt[qt * kBM + ql];
-      if (lane == 0 && ew == 0) s_touched[qt] = 1;   // (the groups may meet different query tiles)
-      // Shared threshold: every CTA that holds k_sel candidates for this query publishes its k_sel-th
-      // score (atomicMax below).  The global k_sel-th best is >= each of them, so anything strictly
-      // below the published maximum can be skipped by everybody; without this each of the ~37 CTAs
-      // serving a query tile warms its threshold up on its own and collects ~37x more candidates.
-      const int64_t gq = static_cast<int64_t>(qt) * kBM + ql;
-      uint32_t* gthr = p.shared_thr + (gq < p.nq ? gq : 0);
-      const uint32_t g_pub = cur.g_pub;
       const int64_t row0 = static_cast<int64_t>(p.tile_begin + t) * kBN + col0;
       STAT_T(e0);
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -773,7 +807,6 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBN + col0);
       uint32_t va[32], vb[32];
       tmem_ld_32x32(taddr0, va);  // first chunk on its way before anything else is looked at
-      if (gq < p.nq && g_pub > 1u) thr = fmaxf(thr, ordered_to_f32(g_pub - 1u));  // keep scores >= published
       STAT_ADD(9, 1);
 #ifdef PVDB_BATCH_STATS
       const int cnt_before_visit = cnt;
@@ -784,7 +817,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         float* drow = p.dump + static_cast<size_t>(gq) * p.dump_ld + (static_cast<size_t>(t) * kBN + col0);
 #pragma unroll
         for (int cb = 0; cb < kChunks; ++cb) {
-          const uint32_t mw = __shfl_sync(0xffffffffu, cur.mw, cb);
+          const uint32_t mw = __shfl_sync(0xffffffffu, cur_mw, cb);
           tmem_ld_wait(va);
 #pragma unroll
           for (int j = 0; j < 32; ++j) vb[j] = ((mw >> j) & 1u) ? va[j] : 0xff800000u;
@@ -797,7 +830,7 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll 1
       for (int cb = 0; cb < kChunks; cb += 2) {
         // mask words of the two 32-column chunks of this step (warp-uniform)
-        const uint32_t mw0 = __shfl_sync(0xffffffffu, cur.mw, cb), mw1 = __shfl_sync(0xffffffffu, cur.mw, cb + 1);
+        const uint32_t mw0 = __shfl_sync(0xffffffffu, cur_mw, cb), mw1 = __shfl_sync(0xffffffffu, cur_mw, cb + 1);
         // chunk cb is in flight into `va`; start chunk cb+1 into `vb` before examining `va`
         STAT_T(w0);
         tmem_ld_wait(va);
@@ -830,7 +863,13 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             pruned_away += c - nc;
 #endif
             cnt = nc;
-            if (nt > thr) thr = nt;
+            if (nt > thr) {
+              thr = nt;
+              // The other group may be a visit ahead or behind, so a bound proven here is shared
+              // NON-strictly (one ulp lower): a row with exactly the k_sel-th score must not be dropped
+              // there, it could have the lower row number and win the tie.
+              atomicMax(&s_thr[sidx], f32_to_ordered(nt) - 1u);
+            }
             if (c >= p.k_sel) atomicMax(gthr, f32_to_ordered(nt));
           }
           __syncwarp();
@@ -846,12 +885,12 @@ batch_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
       }
 #endif
       release_accumulator();
-      // The other group may be a visit ahead or behind, so a bound proven here is shared NON-strictly
-      // (one ulp lower): a row with exactly the k_sel-th score must not be dropped there, it could
-      // have the lower row number and win the tie.
-      const uint32_t thr_out = f32_to_ordered(thr) - 1u;
-      if (thr_out > thr_in) atomicMax(&s_thr[qt * kBM + ql], thr_out);
-      my_cnt[qt * kBM + ql] = static_cast<uint16_t>(cnt);
+      if (last) {
+        // ---- the item ends: hand the state back (bounds taken from elsewhere travel on, non-strictly)
+        const uint32_t thr_out = f32_to_ordered(thr) - 1u;
+        if (thr_out > thr_in) atomicMax(&s_thr[sidx], thr_out);
+        my_cnt[sidx] = static_cast<uint16_t>(cnt);
+      }
     }
     STAT_ADD(0, clock64() - e_begin);
     // all visits done: the pools stay as they are (finalize filters and sorts); publish their counts
@@ -1280,26 +1319,25 @@ static int encode_map(CUtensorMap* map, bool bf16, const void* base, int inner, 
 }
 
 // Kernel variant for (element type, cluster size, pair MMA, pool size).
-template <bool BF16, int CL, bool PAIR, bool ALT>
+template <bool BF16, int CL, bool PAIR>
 static const void* batch_kernel_ptr(int pool_cap) {
-  return pool_cap == 128 ? reinterpret_cast<const void*>(batch_topk_kernel<BF16, 4, CL, PAIR, ALT>)
-                         : reinterpret_cast<const void*>(batch_topk_kernel<BF16, 8, CL, PAIR, ALT>);
+  return pool_cap == 128 ? reinterpret_cast<const void*>(batch_topk_kernel<BF16, 4, CL, PAIR>)
+                         : reinterpret_cast<const void*>(batch_topk_kernel<BF16, 8, CL, PAIR>);
 }
 
-template <bool BF16, bool ALT>
+template <bool BF16>
 static const void* batch_kernel_cl(int cl, bool pair, int pool_cap) {
-  if (pair) return batch_kernel_ptr<BF16, 2, true, false>(pool_cap);
+  if (pair) return batch_kernel_ptr<BF16, 2, true>(pool_cap);
   switch (cl) {
-    case 8: return batch_kernel_ptr<BF16, 8, false, ALT>(pool_cap);
-    case 4: return batch_kernel_ptr<BF16, 4, false, ALT>(pool_cap);
-    case 2: return batch_kernel_ptr<BF16, 2, false, ALT>(pool_cap);
-    default: return batch_kernel_ptr<BF16, 1, false, ALT>(pool_cap);
+    case 8: return batch_kernel_ptr<BF16, 8, false>(pool_cap);
+    case 4: return batch_kernel_ptr<BF16, 4, false>(pool_cap);
+    case 2: return batch_kernel_ptr<BF16, 2, false>(pool_cap);
+    default: return batch_kernel_ptr<BF16, 1, false>(pool_cap);
   }
 }
 
-static const void* batch_kernel(bool bf16, int cl, bool pair, int pool_cap, bool alt) {
-  if (bf16) return alt ? batch_kernel_cl<true, true>(cl, pair, pool_cap) : batch_kernel_cl<true, false>(cl, pair, pool_cap);
-  return alt ? batch_kernel_cl<false, true>(cl, pair, pool_cap) : batch_kernel_cl<false, false>(cl, pair, pool_cap);
+static const void* batch_kernel(bool bf16, int cl, bool pair, int pool_cap) {
+  return bf16 ? batch_kernel_cl<true>(cl, pair, pool_cap) : batch_kernel_cl<false>(cl, pair, pool_cap);
 }
 
 static void batch_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int cl, int grid, cudaStream_t st) {
@@ -1391,9 +1429,9 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
   // cta_group::2 MMAs (one M=256 instruction per CTA pair); PVDB_BATCH_PAIR=0 keeps the multicast variant
   const char* pair_env = getenv("PVDB_BATCH_PAIR");
   const bool pair_mma = pair_env ? atoi(pair_env) != 0 : kPairDefault;
-  // epilogue groups alternate accumulators (each drains whole tiles) instead of splitting every tile
-  const char* alt_env = getenv("PVDB_BATCH_ALT");
-  const bool alt_epilogue = alt_env ? atoi(alt_env) != 0 : kAltDefault;
+  // database tiles per work item (VisitSeq); 0 = choose per pass
+  int tile_block_env = 0;
+  if (const char* e = getenv("PVDB_BATCH_TILE_BLOCK")) tile_block_env = std::min(kMaxTileBlock, std::max(1, atoi(e)));
   const void* db_ptr = use_bf16 ? s->bf16.ptr : s->f32.ptr;
   const int db_ld = use_bf16 ? s->ld_bf16 : s->ld_f32;
 
@@ -1490,15 +1528,22 @@ int search_batch(pvdb_store* s, bool use_bf16, const float* d_qn, const __nv_bfl
         if (p.q_tiles >= c && ((p.q_tiles + c - 1) / c) * c * 4 <= p.q_tiles * 5) cl = c;
       const bool pair = pair_mma && cl >= 2;
       if (pair) cl = 2;
-      const void* kern = batch_kernel(use_bf16, cl, pair, p.pool_cap, alt_epilogue && !dump_scores);
+      const void* kern = batch_kernel(use_bf16, cl, pair, p.pool_cap);
       int max_units = 0;
       PVDB_TRY(batch_max_units(kern, cl, &max_units));
       CUtensorMap mdb;  // box = the rows one CTA fetches per K block
       PVDB_TRY(encode_map(&mdb, use_bf16, db_ptr, k_ext, s->capacity, db_ld, kBN / cl));
-      const int64_t n_visits = static_cast<int64_t>(n_tiles) * ((p.q_tiles + cl - 1) / cl);
-      const int grid = cl * static_cast<int>(std::min<int64_t>(n_visits, max_units));
+      const int n_qp = (p.q_tiles + cl - 1) / cl;
+      const int64_t n_visits = static_cast<int64_t>(n_tiles) * n_qp;
+      // Work items of R consecutive tiles for one query-tile group (VisitSeq): as large as leaves every
+      // unit >= 16 items (the last wave of items is the load imbalance), at most kMaxTileBlock.
+      int tile_block = static_cast<int>(std::min<int64_t>(kMaxTileBlock, n_visits / (16 * static_cast<int64_t>(max_units))));
+      if (tile_block_env > 0) tile_block = tile_block_env;
+      p.tile_block = std::max(1, std::min(tile_block, n_tiles));
+      const int64_t n_items = static_cast<int64_t>((n_tiles + p.tile_block - 1) / p.tile_block) * n_qp;
+      const int grid = cl * static_cast<int>(std::min<int64_t>(n_items, max_units));
       // pinned schedule: stride = (query-tile pairs) x (units per pair), so a unit never changes pair
-      const int n_qp = (p.q_tiles + cl - 1) / cl, n_units = grid / cl;
+      const int n_units = grid / cl;
       p.visit_stride = (pin_query_tiles && n_units >= n_qp) ? n_qp * (n_units / n_qp) : 0;
       PVDB_CUDA(cudaMemsetAsync(p.touched, 0, touched_bytes + thr_bytes, st));
       PVDB_TRY(launch_batch(kern, cl, mq, mdb, p, grid, st));
