@@ -26,6 +26,11 @@ extern template int launch_scan_variant<false, false>(const ScanParams&, int, in
 extern template int launch_scan_variant<false, true>(const ScanParams&, int, int, cudaStream_t);
 extern template int launch_scan_variant<true, false>(const ScanParams&, int, int, cudaStream_t);
 extern template int launch_scan_variant<true, true>(const ScanParams&, int, int, cudaStream_t);
+// defined in scan_inst_bf16_mma_*.cu
+template <bool SPARSE>
+int launch_scan_mma_variant(const ScanParams& p, cudaStream_t stream);
+extern template int launch_scan_mma_variant<false>(const ScanParams&, cudaStream_t);
+extern template int launch_scan_mma_variant<true>(const ScanParams&, cudaStream_t);
 
 int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   if (p.k < 1 || p.k > kFusedK) return fail(PVDB_ERR_INVALID, "scan: k=%d outside [1, %d]", p.k, kFusedK);
@@ -43,6 +48,10 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   const int ch = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
   // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
   const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
+  // bf16 rows of up to 512 columns: dot products on mma.sync (fewer instructions per byte: the chip sustains
+  // more of its HBM bandwidth under the power cap -- see scan_mma_topk_kernel)
+  if (is_bf16 && rc <= 64 && getenv("PVDB_SCAN_NO_MMA") == nullptr)
+    return sparse ? launch_scan_mma_variant<true>(p, stream) : launch_scan_mma_variant<false>(p, stream);
   if (is_bf16) return sparse ? launch_scan_variant<true, true>(p, lpr, ch, stream)
                              : launch_scan_variant<true, false>(p, lpr, ch, stream);
   return sparse ? launch_scan_variant<false, true>(p, lpr, ch, stream)

@@ -30,27 +30,12 @@ __device__ __forceinline__ float dot_chunk_bf16(const uint4& v, const float4& q0
   return acc;
 }
 
-// LPR lanes cooperate on one row; each lane keeps CH 16-byte loads of R rows in flight
-// (CH * R == 8 -> eight independent 128-bit loads per lane per step).
-// S: 32-key slots of the per-warp list (1 for k <= 32 -- cheaper inserts and merges, fewer registers;
-// 4 for k <= 128).
-template <bool BF16, int LPR, int CH, bool SPARSE, int S>
-__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kernel(const ScanParams p) {
-  constexpr int G = 32 / LPR;  // row groups per warp
-  constexpr int R = 8 / CH;    // rows in flight per group
-  constexpr int RPW = G * R;   // rows per warp step: a power of two <= 32, so one bitmap word covers it
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* sq = reinterpret_cast<float*>(smem_raw);
-  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
-  __shared__ unsigned s_is_last;
-
+// What every scan variant does first: programmatic-dependent-launch bookkeeping, then the normalised query
+// goes to shared memory (sq[0 .. query_floats), zero padded).
+__device__ __forceinline__ void scan_prologue(const ScanParams& p, float* sq) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int sub = lane % LPR;
-  const int gi = lane / LPR;
-  const int k = p.k;
-
   // Programmatic dependent launch: let the next scan on the stream start filling SMs as soon as this
   // grid's blocks retire (its scan phase only reads the matrix), and wait for the PREVIOUS grid only
   // where this one touches what that one may still be using (below: paging bound, per-block lists).
@@ -66,7 +51,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     // (lane-strided fp32 partial sums of ONE warp, fp64 butterfly), so a query is normalised to the
     // same bits whether it arrives alone or inside a batch.
     __shared__ float s_nrm;
-    for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = (i < p.dim) ? p.raw_query[i] : 0.f;
+    for (int i = tid; i < p.query_floats; i += static_cast<int>(blockDim.x)) sq[i] = (i < p.dim) ? p.raw_query[i] : 0.f;
     __syncthreads();
     if (warp == 0) {
       float ss = 0.f;
@@ -81,14 +66,144 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     }
     __syncthreads();
     const float nrm = s_nrm;
-    for (int i = tid; i < p.query_floats; i += kScanThreads) {
+    for (int i = tid; i < p.query_floats; i += static_cast<int>(blockDim.x)) {
       const float x = sq[i];
       sq[i] = (nrm == 0.f) ? (i == 0 ? 1.f : 0.f) : __fdiv_rn(x, nrm);
     }
   } else {
-    for (int i = tid; i < p.query_floats; i += kScanThreads) sq[i] = p.query[i];
+    for (int i = tid; i < p.query_floats; i += static_cast<int>(blockDim.x)) sq[i] = p.query[i];
   }
   __syncthreads();
+}
+
+// What every scan variant does last: block merge of the warp lists, last-block-done merge of the per-block
+// lists, optional cross-GPU exchange, result write-out.
+template <int S>
+__device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L, uint64_t& thr, uint64_t* slist) {
+  __shared__ unsigned s_is_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int k = p.k;
+  const int n_warps = static_cast<int>(blockDim.x >> 5);   // (the mma variant runs smaller blocks)
+  // ---- block merge: warp 0 folds the other warps' lists into its own
+  store_list(L, slist + warp * k, k, lane);
+  __syncthreads();
+  // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (warp == 0) {
+    for (int w2 = 1; w2 < n_warps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
+    store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned t = atomicAdd(p.ticket, 1u);
+      s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
+  }
+  __syncthreads();
+  if (s_is_last == 0u) return;
+
+  // ---- last block: merge all per-block lists and emit the result
+  __threadfence();
+  L.clear();
+  thr = 0ull;
+  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
+  // together so the L2 round trips overlap; a list whose whole head qualified continues through
+  // the general path.
+  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += n_warps * 8) {
+    uint64_t head[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * n_warps;
+      head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
+                    ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
+                    : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * n_warps;
+      if (b >= static_cast<int>(gridDim.x)) break;
+      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
+      const bool head_all = (m == 0xffffffffu);
+      while (m) {
+        const int srcl = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t x = shfl_u64(head[j], srcl);
+        if (x > thr) {
+          L.insert(x, lane);
+          thr = L.get(k - 1);
+        }
+      }
+      if (head_all && k > 32) merge_list<true, S>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
+    }
+  }
+  __syncthreads();  // everyone is done reading slist from the first merge
+  store_list(L, slist + warp * k, k, lane);
+  __syncthreads();
+  if (warp == 0) {
+    for (int w2 = 1; w2 < n_warps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
+    int64_t out_base = p.row_base;
+    if (p.xv.world > 0) {
+      // ---- cross-GPU exchange, fused (exchange.cuh): this GPU's list goes into every peer's
+      // mailbox as keys with global rows, the peers' lists arrive in ours, and the k-way merge of
+      // the `world` lists happens right here -- the kernel writes the FINAL top k on every GPU.
+      const ExchangeView& v = p.xv;
+      const int parity = static_cast<int>(v.seq & 1ull);
+      for (int peer = 0; peer < v.world; ++peer) {
+        uint64_t* dst = xv_slot(v, v.box[peer], parity, v.rank);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int e = s * 32 + lane;
+          if (e < k) dst[e] = key_to_global(L.slot[s], p.row_base);
+        }
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane < v.world) st_release_sys(xv_flag(v.box[lane], parity, v.rank, 0), v.seq);
+      if (lane < v.world) xv_wait_flag(xv_flag(v.box[v.rank], parity, lane, 0), v.seq);
+      __syncwarp();
+      L.clear();
+      thr = 0ull;
+      for (int r = 0; r < v.world; ++r) merge_list<true, S>(L, thr, xv_slot(v, v.box[v.rank], parity, r), k, k, lane);
+      out_base = 0;  // the merged keys carry global rows
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      const int e = s * 32 + lane;
+      if (e < k) {
+        const uint64_t key = L.slot[s];
+        p.out_scores[e] = key ? key_score(key) : -INFINITY;
+        p.out_rows[e] = key ? out_base + static_cast<int64_t>(key_row(key)) : -1ll;
+      }
+    }
+    const uint64_t kth = L.get(k - 1);
+    if (lane == 0) {
+      *p.next_upper = kth;
+      *p.ticket = 0u;
+    }
+  }
+}
+
+// LPR lanes cooperate on one row; each lane keeps CH 16-byte loads of R rows in flight
+// (CH * R == 8 -> eight independent 128-bit loads per lane per step).
+// S: 32-key slots of the per-warp list (1 for k <= 32 -- cheaper inserts and merges, fewer registers;
+// 4 for k <= 128).
+template <bool BF16, int LPR, int CH, bool SPARSE, int S>
+__global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kernel(const ScanParams p) {
+  constexpr int G = 32 / LPR;  // row groups per warp
+  constexpr int R = 8 / CH;    // rows in flight per group
+  constexpr int RPW = G * R;   // rows per warp step: a power of two <= 32, so one bitmap word covers it
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int sub = lane % LPR;
+  const int gi = lane / LPR;
+  const int k = p.k;
+
+  scan_prologue(p, sq);
   const float4* sq4 = reinterpret_cast<const float4*>(sq);
 
   const uint64_t upper = p.upper ? *p.upper : ~0ull;
@@ -209,105 +324,212 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
     }
   }
 
-  // ---- block merge: warp 0 folds the other warps' lists into its own
-  store_list(L, slist + warp * k, k, lane);
-  __syncthreads();
-  // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
-    store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) {
-      const unsigned t = atomicAdd(p.ticket, 1u);
-      s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+  scan_finish<S>(p, L, thr, slist);
+}
+
+
+
+// ---------------------------------------------------------------------------- bf16 rows on the legacy tensor-core path
+// scan_mma_topk_kernel: the same single-query scan for a bf16 matrix of dim <= 512, with the dot products
+// on mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  WHY: the scan is HBM bound, but under the 1 kW power cap the
+// SM clock -- and with it what the chip sustains from HBM -- depends on how many instructions ride on each
+// byte (tools/micro/hbm_read_sustained.cu, random data, 600 back-to-back launches: 8 FMA per 16-byte chunk
+// 6.90 TB/s, 16: 6.81, 32: 6.25).  The CUDA-core form spends ~22 instructions per chunk (8 shifts / masks to
+// widen bf16, 8 FMA, query reads from shared memory) and sustains 6.0-6.4 TB/s on the 100M x 384 store; this
+// form spends one load and one MMA per chunk.
+//   * A warp step scores 16 rows.  Thread (g = lane / 4, t = lane % 4) loads, for each 32-column slice, the
+//     16 bytes at columns [8 t, 8 t + 8) of row g and of row g + 8: exactly the A fragments of TWO MMAs (the
+//     k index inside a fragment is only a label, so "logical k = 2t, 2t+1, 2t+8, 2t+9" is mapped to this
+//     thread's four consecutive columns; the query fragments use the same mapping).
+//   * EXACTNESS.  The fp32 query is split into three bf16 terms q = hi + mid + lo (24 mantissa bits: exact)
+//     which ride in columns 0, 1, 2 of the B operand; the other five columns are zero.  Every product
+//     bf16 x bf16 is exact in fp32 and the accumulators are fp32, so a score differs from the CUDA-core
+//     kernel's only by the order of the fp32 additions (~1e-7 for unit vectors; tests hold it to the same
+//     1e-5 / 2e-6 tolerance against the oracle).
+//   * The query fragments stay in REGISTERS (4 per slice: no shared-memory traffic in the loop).
+// KS: 32-column slices held in registers (dim <= 32 KS).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// part 0 / 1 / 2 of the three-term bf16 split of x (bit pattern in the low 16 bits)
+__device__ __forceinline__ uint32_t bf16_split_part(float x, int part) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(mid);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r2);
+  const __nv_bfloat16 pick = part == 0 ? hi : (part == 1 ? mid : lo);
+  return static_cast<uint32_t>(__bfloat16_as_ushort(pick));
+}
+
+constexpr int kScanMmaThreads = 256;   // x 2 blocks per SM: up to 128 registers per thread (48-64 hold the query fragments)
+constexpr int kScanMmaWarps = kScanMmaThreads / 32;
+
+template <bool SPARSE, int S, int KS>
+__global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_topk_kernel(const ScanParams p) {
+  constexpr int RPW = 16;  // rows per warp step (the M of the MMA)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int g = lane >> 2;   // fragment row (and the B column this thread feeds)
+  const int t = lane & 3;    // which 8 columns of every 32-column slice
+  const int k = p.k;
+
+  scan_prologue(p, sq);
+
+  // query fragments: slice ks, this thread's columns c0 = 32 ks + 8 t ... c0 + 7 as four bf16 pairs of
+  // part g of the split (threads with g >= 3 feed the unused B columns: zeros)
+  uint32_t bq[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = ks * 32 + t * 8 + 2 * j;
+      uint32_t w = 0u;
+      if (g < 3 && c < p.query_floats) {
+        const float x0 = sq[c];
+        const float x1 = (c + 1 < p.query_floats) ? sq[c + 1] : 0.f;
+        w = bf16_split_part(x0, g) | (bf16_split_part(x1, g) << 16);
+      }
+      bq[ks][j] = w;
     }
   }
-  __syncthreads();
-  if (s_is_last == 0u) return;
 
-  // ---- last block: merge all per-block lists and emit the result
-  __threadfence();
+  const uint64_t upper = p.upper ? *p.upper : ~0ull;
+  WarpList<S> L;
   L.clear();
-  thr = 0ull;
-  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
-  // together so the L2 round trips overlap; a list whose whole head qualified continues through
-  // the general path.
-  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += kScanWarps * 8) {
-    uint64_t head[8];
+  uint64_t thr = 0ull;
+
+  const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanMmaWarps;
+  const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
+  const int row_chunks = p.row_chunks;
+
+  // Score the 16 row slots of a warp step (this thread: slots g and g + 8) and feed the warp list.
+  auto score_rows = [&](const int64_t (&row)[2], const bool (&on)[2]) {
+    const uint4* rp0 = mat + row[0] * row_chunks + t;
+    const uint4* rp1 = mat + row[1] * row_chunks + t;
+    float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = b0 + j * kScanWarps;
-      head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
-                    ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
-                    : 0ull;
+    for (int ks0 = 0; ks0 < KS; ks0 += 4) {
+      if (ks0 * 4 >= row_chunks) break;   // (warp-uniform) slices past the row
+      uint4 v0[4], v1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ks = ks0 + i;
+        const bool in = ks < KS && ks * 4 + t < row_chunks;
+        v0[i] = (on[0] && in) ? ldg_stream(rp0 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+        v1[i] = (on[1] && in) ? ldg_stream(rp1 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ks = ks0 + i;
+        if (ks < KS) {
+          mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, bq[ks][0], bq[ks][1]);
+          mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, bq[ks][2], bq[ks][3]);
+        }
+      }
     }
+    // thread t == 0 holds (hi, mid) of rows g / g + 8 in c[0..1] / c[2..3]; thread t == 1 holds lo in c[0] / c[2]
+    const float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2], c3 = ca[3] + cb[3];
+    const float lo0 = __shfl_down_sync(0xffffffffu, c0, 1), lo1 = __shfl_down_sync(0xffffffffu, c2, 1);
+    const float sc[2] = {(lo0 + c1) + c0, (lo1 + c3) + c2};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int b = b0 + j * kScanWarps;
-      if (b >= static_cast<int>(gridDim.x)) break;
-      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
-      const bool head_all = (m == 0xffffffffu);
+    for (int r = 0; r < 2; ++r) {
+      const uint64_t key = (on[r] && sc[r] == sc[r]) ? make_key(sc[r], static_cast<uint32_t>(row[r])) : 0ull;
+      unsigned m = __ballot_sync(0xffffffffu, t == 0 && key > thr && key < upper);
       while (m) {
         const int srcl = __ffs(m) - 1;
         m &= m - 1;
-        const uint64_t x = shfl_u64(head[j], srcl);
+        const uint64_t x = shfl_u64(key, srcl);
         if (x > thr) {
           L.insert(x, lane);
           thr = L.get(k - 1);
         }
       }
-      if (head_all && k > 32) merge_list<true, S>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
     }
-  }
-  __syncthreads();  // everyone is done reading slist from the first merge
-  store_list(L, slist + warp * k, k, lane);
-  __syncthreads();
-  if (warp == 0) {
-    for (int w2 = 1; w2 < kScanWarps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
-    int64_t out_base = p.row_base;
-    if (p.xv.world > 0) {
-      // ---- cross-GPU exchange, fused (exchange.cuh): this GPU's list goes into every peer's
-      // mailbox as keys with global rows, the peers' lists arrive in ours, and the k-way merge of
-      // the `world` lists happens right here -- the kernel writes the FINAL top k on every GPU.
-      const ExchangeView& v = p.xv;
-      const int parity = static_cast<int>(v.seq & 1ull);
-      for (int peer = 0; peer < v.world; ++peer) {
-        uint64_t* dst = xv_slot(v, v.box[peer], parity, v.rank);
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          const int e = s * 32 + lane;
-          if (e < k) dst[e] = key_to_global(L.slot[s], p.row_base);
-        }
-      }
-      __threadfence_system();
-      __syncwarp();
-      if (lane < v.world) st_release_sys(xv_flag(v.box[lane], parity, v.rank, 0), v.seq);
-      if (lane < v.world) xv_wait_flag(xv_flag(v.box[v.rank], parity, lane, 0), v.seq);
-      __syncwarp();
-      L.clear();
-      thr = 0ull;
-      for (int r = 0; r < v.world; ++r) merge_list<true, S>(L, thr, xv_slot(v, v.box[v.rank], parity, r), k, k, lane);
-      out_base = 0;  // the merged keys carry global rows
+  };
+
+  if constexpr (!SPARSE) {
+    // dense walk: a warp step covers 16 consecutive rows (half a bitmap word)
+    const int64_t n_steps = (p.n_rows + RPW - 1) / RPW;
+    for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanMmaWarps + warp; step < n_steps; step += total_warps) {
+      const int64_t base = step * RPW;
+      uint32_t w = __ldg(p.active + (base >> 5));
+      if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
+      w = (w >> (base & 31)) & 0xffffu;
+      if (w == 0u) continue;  // every row of this step is deleted / filtered out: read nothing
+      const int64_t row[2] = {base + g, base + g + 8};
+      const bool on[2] = {((w >> g) & 1u) != 0u, ((w >> (g + 8)) & 1u) != 0u};
+      score_rows(row, on);
     }
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int e = s * 32 + lane;
-      if (e < k) {
-        const uint64_t key = L.slot[s];
-        p.out_scores[e] = key ? key_score(key) : -INFINITY;
-        p.out_rows[e] = key ? out_base + static_cast<int64_t>(key_row(key)) : -1ll;
+  } else {
+    // sparse walk (selective prefilters): one bitmap word = 32 consecutive rows at a time, only the SET
+    // bits are packed into the 16 row slots
+    const int64_t n_words = (p.n_rows + 31) >> 5;
+    for (int64_t wi = static_cast<int64_t>(blockIdx.x) * kScanMmaWarps + warp; wi < n_words; wi += total_warps) {
+      uint32_t w = __ldg(p.active + wi);
+      if (w != 0u && p.prefilter) w &= __ldg(p.prefilter + wi);
+      while (w != 0u) {
+        const unsigned b0 = __fns(w, 0, g + 1), b1 = __fns(w, 0, g + 9);  // positions of this thread's slots' set bits
+        const bool on[2] = {b0 < 32u, b1 < 32u};
+        const int64_t row[2] = {(wi << 5) + (on[0] ? b0 : 0u), (wi << 5) + (on[1] ? b1 : 0u)};
+        score_rows(row, on);
+        const unsigned last = __fns(w, 0, RPW);  // drop the 16 lowest set bits that were just consumed
+        w = (last < 31u) ? (w & (0xffffffffu << (last + 1))) : 0u;
       }
     }
-    const uint64_t kth = L.get(k - 1);
-    if (lane == 0) {
-      *p.next_upper = kth;
-      *p.ticket = 0u;
-    }
   }
+  scan_finish<S>(p, L, thr, slist);
 }
 
+template <bool SPARSE, int S, int KS>
+static int launch_scan_mma_inst(const ScanParams& p, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
+                      static_cast<size_t>(kScanMmaWarps) * p.k * sizeof(uint64_t);
+  auto kern = scan_mma_topk_kernel<SPARSE, S, KS>;
+  if (smem > 48 * 1024)
+    PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(kNumSMs * kScanBlocksPerSM);
+    cfg.blockDim = dim3(kScanMmaThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PVDB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<kNumSMs * kScanBlocksPerSM, kScanMmaThreads, smem, stream>>>(p);
+  }
+  PVDB_LAUNCH_CHECK();
+  return PVDB_OK;
+}
+
+// bf16 rows of at most 512 columns (row_chunks <= 64)
+template <bool SPARSE>
+int launch_scan_mma_variant(const ScanParams& p, cudaStream_t stream) {
+  const int ks = (p.row_chunks + 3) / 4;
+  if (p.k <= 32) {
+    if (ks <= 4) return launch_scan_mma_inst<SPARSE, 1, 4>(p, stream);
+    if (ks <= 8) return launch_scan_mma_inst<SPARSE, 1, 8>(p, stream);
+    if (ks <= 12) return launch_scan_mma_inst<SPARSE, 1, 12>(p, stream);
+    return launch_scan_mma_inst<SPARSE, 1, 16>(p, stream);
+  }
+  if (ks <= 4) return launch_scan_mma_inst<SPARSE, 4, 4>(p, stream);
+  if (ks <= 8) return launch_scan_mma_inst<SPARSE, 4, 8>(p, stream);
+  if (ks <= 12) return launch_scan_mma_inst<SPARSE, 4, 12>(p, stream);
+  return launch_scan_mma_inst<SPARSE, 4, 16>(p, stream);
+}
 
 // Launch the (LPR, CH, S) instantiation for this translation unit's (BF16, SPARSE).
 template <bool BF16, bool SPARSE, int LPR, int CH, int S>

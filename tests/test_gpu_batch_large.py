@@ -96,3 +96,31 @@ def test_batch_results_do_not_depend_on_timing(store_factory):
             else:
                 np.testing.assert_array_equal(rows, first[1])
                 np.testing.assert_array_equal(sc, first[0])
+
+
+@pytest.mark.parametrize("env", [
+    {"PVDB_BATCH_TILE_BLOCK": "1"},
+    {"PVDB_BATCH_TILE_BLOCK": "3"},
+    {"PVDB_BATCH_TILE_BLOCK": "8"},
+    {"PVDB_BATCH_TILE_BLOCK": "5", "PVDB_BATCH_NO_CLUSTER": "1"},
+    {"PVDB_BATCH_TILE_BLOCK": "4", "PVDB_BATCH_PAIR": "1"},
+    {"PVDB_BATCH_TILE_BLOCK": "7", "PVDB_BATCH_CLUSTER": "4"},
+])
+def test_work_item_schedules_give_the_same_answer(store_factory, monkeypatch, env):
+    """Visits are grouped into work items of R consecutive database tiles per query tile (VisitSeq in
+    csrc/batch.cu); R, the cluster size and the pair-MMA variant only change WHO scores WHICH tile WHEN.
+    Every schedule must return the oracle's rows -- tile counts that are not multiples of R, an odd number
+    of query tiles (padding tile in a cluster) and a prefilter included."""
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    dim, n, nq, k = 48, 150_001, 1100, 10   # 586 tiles (last one partial), 9 query tiles
+    s = store_factory(dim, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 25), 0)
+    store = s.download()
+    qn, _ = O.prepare_queries(_gauss(nq, dim, 27), dim)
+    pf = (np.arange(n) % 5) != 2
+    ref_s, ref_r = O.search_chunked(store, qn, k, None, pf)
+    for prec in ("tf32", "bf16"):
+        sc, rows = s.search(qn, k, prefilter=pf, precision=prec, normalized=True)
+        _check(sc, rows, store, qn, k, ref_s, ref_r, 0.995)
+        assert pf[rows].all()

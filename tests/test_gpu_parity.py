@@ -653,3 +653,42 @@ def test_concurrent_searches_on_one_store(store_factory):
     for th in threads:
         th.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.parametrize("dim", [8, 24, 100, 128, 200, 384, 500, 512])
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_bf16_scan_on_mma_matches_the_cuda_core_scan_and_the_exact_dot(store_factory, monkeypatch, dim, k):
+    """bf16 rows of up to 512 columns are scored on mma.sync with the fp32 query split into three bf16 terms
+    (scan_mma_topk_kernel).  Products are exact and accumulation is fp32, so the scores must agree with the
+    CUDA-core kernel (PVDB_SCAN_NO_MMA=1) and with the float64 dot product of the stored bf16 rows to ~1e-6
+    -- the fp32 tolerance, not the bf16 one -- with deleted rows, a dense and a sparse (prefilter) walk."""
+    n = 5003
+    s = store_factory(dim, keep_f32=False, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 300 + dim), 0)
+    dead = np.random.default_rng(3).choice(n, n // 7, replace=False)
+    s.delete_rows(dead)
+    rows_f32 = s.download()                      # the stored bf16 values, widened
+    active = np.ones(n, bool)
+    active[dead] = False
+    pf = (np.arange(n) % 3) != 1
+    queries = _gauss(4, dim, 11)
+    queries[2] = 0.0
+    qn, _ = O.prepare_queries(queries, dim)
+    for prefilter in (None, pf):
+        live = active if prefilter is None else (active & prefilter)
+        for qi in range(4):
+            exact = rows_f32.astype(np.float64) @ qn[qi].astype(np.float64)
+            exact[~live] = -np.inf
+            monkeypatch.delenv("PVDB_SCAN_NO_MMA", raising=False)
+            sc, rows = s.search(queries[qi:qi + 1], k, prefilter=prefilter)
+            monkeypatch.setenv("PVDB_SCAN_NO_MMA", "1")
+            sc_c, rows_c = s.search(queries[qi:qi + 1], k, prefilter=prefilter)
+            monkeypatch.delenv("PVDB_SCAN_NO_MMA", raising=False)
+            assert np.all(np.diff(sc[0]) <= 0)
+            assert live[rows[0]].all()
+            np.testing.assert_allclose(sc[0], exact[rows[0]], rtol=F32_RTOL, atol=F32_ATOL)
+            np.testing.assert_allclose(sc[0], sc_c[0], rtol=F32_RTOL, atol=F32_ATOL)
+            # the same rows, except where two scores are closer than the accumulation-order noise
+            kth = np.sort(exact)[::-1][k - 1]
+            for r in set(rows[0].tolist()) ^ set(rows_c[0].tolist()):
+                assert abs(exact[r] - kth) <= 4e-6, (r, exact[r], kth)
