@@ -48,9 +48,9 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   const int ch = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
   // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
   const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
-  // bf16 rows of up to 512 columns: dot products on mma.sync (fewer instructions per byte: the chip sustains
-  // more of its HBM bandwidth under the power cap -- see scan_mma_topk_kernel)
-  if (is_bf16 && rc <= 64 && getenv("PVDB_SCAN_NO_MMA") == nullptr)
+  // bf16 rows: dot products on mma.sync (fewer instructions per byte: the chip sustains more of its HBM
+  // bandwidth under the power cap -- see scan_mma_topk_kernel)
+  if (is_bf16 && getenv("PVDB_SCAN_NO_MMA") == nullptr)
     return sparse ? launch_scan_mma_variant<true>(p, stream) : launch_scan_mma_variant<false>(p, stream);
   if (is_bf16) return sparse ? launch_scan_variant<true, true>(p, lpr, ch, stream)
                              : launch_scan_variant<true, false>(p, lpr, ch, stream);

@@ -346,8 +346,10 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
 //     bf16 x bf16 is exact in fp32 and the accumulators are fp32, so a score differs from the CUDA-core
 //     kernel's only by the order of the fp32 additions (~1e-7 for unit vectors; tests hold it to the same
 //     1e-5 / 2e-6 tolerance against the oracle).
-//   * The query fragments stay in REGISTERS (4 per slice: no shared-memory traffic in the loop).
-// KS: 32-column slices held in registers (dim <= 32 KS).
+//   * The query fragments stay in REGISTERS (4 per slice: no shared-memory traffic in the loop) for
+//     dim <= 512; wider rows (KS == 0) read them from shared memory, one 16-byte load per slice and thread
+//     (half the shared-memory bytes of the CUDA-core kernel and none of its arithmetic).
+// KS: 32-column slices held in registers (dim <= 32 KS); 0 = any width, fragments in shared memory.
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                uint32_t b1) {
   asm volatile(
@@ -373,9 +375,15 @@ constexpr int kScanMmaWarps = kScanMmaThreads / 32;
 template <bool SPARSE, int S, int KS>
 __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_topk_kernel(const ScanParams p) {
   constexpr int RPW = 16;  // rows per warp step (the M of the MMA)
+  constexpr bool QS = KS == 0;   // query fragments in shared memory
+  constexpr int KR = QS ? 1 : KS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);
   uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
+  // QS: [3 parts][n_slices * 16] packed bf16 pairs behind the lists (8 warps x k keys x 8 bytes: 16-byte aligned)
+  static_assert((kScanMmaWarps * sizeof(uint64_t)) % 16 == 0, "the fragment words must stay 16-byte aligned");
+  uint32_t* sfrag = reinterpret_cast<uint32_t*>(slist + static_cast<size_t>(kScanMmaWarps) * p.k);
+  const int n_slices = (p.row_chunks + 3) / 4;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int g = lane >> 2;   // fragment row (and the B column this thread feeds)
@@ -386,21 +394,35 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
 
   // query fragments: slice ks, this thread's columns c0 = 32 ks + 8 t ... c0 + 7 as four bf16 pairs of
   // part g of the split (threads with g >= 3 feed the unused B columns: zeros)
-  uint32_t bq[KS][4];
+  uint32_t bq[KR][4];
+  if constexpr (!QS) {
 #pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
+    for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = ks * 32 + t * 8 + 2 * j;
-      uint32_t w = 0u;
-      if (g < 3 && c < p.query_floats) {
-        const float x0 = sq[c];
-        const float x1 = (c + 1 < p.query_floats) ? sq[c + 1] : 0.f;
-        w = bf16_split_part(x0, g) | (bf16_split_part(x1, g) << 16);
+      for (int j = 0; j < 4; ++j) {
+        const int c = ks * 32 + t * 8 + 2 * j;
+        uint32_t w = 0u;
+        if (g < 3 && c < p.query_floats) {
+          const float x0 = sq[c];
+          const float x1 = (c + 1 < p.query_floats) ? sq[c + 1] : 0.f;
+          w = bf16_split_part(x0, g) | (bf16_split_part(x1, g) << 16);
+        }
+        bq[ks][j] = w;
       }
-      bq[ks][j] = w;
     }
+  } else {
+    // word i of part q covers columns 2 i, 2 i + 1
+    const int words = n_slices * 16;
+    for (int i = threadIdx.x; i < 3 * words; i += kScanMmaThreads) {
+      const int part = i / words, c = 2 * (i - part * words);
+      const float x0 = c < p.query_floats ? sq[c] : 0.f;
+      const float x1 = c + 1 < p.query_floats ? sq[c + 1] : 0.f;
+      sfrag[i] = bf16_split_part(x0, part) | (bf16_split_part(x1, part) << 16);
+    }
+    __syncthreads();
   }
+  // this thread's fragment words of slice ks sit at sfrag4[ks * 4] (threads with g >= 3 feed zero columns)
+  const uint4* sfrag4 = reinterpret_cast<const uint4*>(sfrag + (g < 3 ? g : 0) * n_slices * 16) + t;
 
   const uint64_t upper = p.upper ? *p.upper : ~0ull;
   WarpList<S> L;
@@ -416,23 +438,45 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
     const uint4* rp0 = mat + row[0] * row_chunks + t;
     const uint4* rp1 = mat + row[1] * row_chunks + t;
     float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (!QS) {
 #pragma unroll
-    for (int ks0 = 0; ks0 < KS; ks0 += 4) {
-      if (ks0 * 4 >= row_chunks) break;   // (warp-uniform) slices past the row
-      uint4 v0[4], v1[4];
+      for (int ks0 = 0; ks0 < KS; ks0 += 4) {
+        if (ks0 * 4 >= row_chunks) break;   // (warp-uniform) slices past the row
+        uint4 v0[4], v1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ks = ks0 + i;
-        const bool in = ks < KS && ks * 4 + t < row_chunks;
-        v0[i] = (on[0] && in) ? ldg_stream(rp0 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
-        v1[i] = (on[1] && in) ? ldg_stream(rp1 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+        for (int i = 0; i < 4; ++i) {
+          const int ks = ks0 + i;
+          const bool in = ks < KS && ks * 4 + t < row_chunks;
+          v0[i] = (on[0] && in) ? ldg_stream(rp0 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+          v1[i] = (on[1] && in) ? ldg_stream(rp1 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ks = ks0 + i;
+          if (ks < KS) {
+            mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, bq[ks][0], bq[ks][1]);
+            mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, bq[ks][2], bq[ks][3]);
+          }
+        }
       }
+    } else {
+      for (int ks0 = 0; ks0 < n_slices; ks0 += 4) {
+        uint4 v0[4], v1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int ks = ks0 + i;
-        if (ks < KS) {
-          mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, bq[ks][0], bq[ks][1]);
-          mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, bq[ks][2], bq[ks][3]);
+        for (int i = 0; i < 4; ++i) {
+          const int ks = ks0 + i;
+          const bool in = ks * 4 + t < row_chunks;
+          v0[i] = (on[0] && in) ? ldg_stream(rp0 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+          v1[i] = (on[1] && in) ? ldg_stream(rp1 + ks * 4) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ks = ks0 + i;
+          if (ks < n_slices) {
+            const uint4 f = g < 3 ? sfrag4[ks * 4] : make_uint4(0u, 0u, 0u, 0u);
+            mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, f.x, f.y);
+            mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, f.z, f.w);
+          }
         }
       }
     }
@@ -491,8 +535,9 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
 
 template <bool SPARSE, int S, int KS>
 static int launch_scan_mma_inst(const ScanParams& p, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
-                      static_cast<size_t>(kScanMmaWarps) * p.k * sizeof(uint64_t);
+  size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
+                static_cast<size_t>(kScanMmaWarps) * p.k * sizeof(uint64_t);
+  if (KS == 0) smem += static_cast<size_t>(3) * ((p.row_chunks + 3) / 4) * 16 * sizeof(uint32_t);
   auto kern = scan_mma_topk_kernel<SPARSE, S, KS>;
   if (smem > 48 * 1024)
     PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -515,7 +560,7 @@ static int launch_scan_mma_inst(const ScanParams& p, cudaStream_t stream) {
   return PVDB_OK;
 }
 
-// bf16 rows of at most 512 columns (row_chunks <= 64)
+// bf16 rows: up to 512 columns with the query fragments in registers, wider rows with them in shared memory
 template <bool SPARSE>
 int launch_scan_mma_variant(const ScanParams& p, cudaStream_t stream) {
   const int ks = (p.row_chunks + 3) / 4;
@@ -523,12 +568,14 @@ int launch_scan_mma_variant(const ScanParams& p, cudaStream_t stream) {
     if (ks <= 4) return launch_scan_mma_inst<SPARSE, 1, 4>(p, stream);
     if (ks <= 8) return launch_scan_mma_inst<SPARSE, 1, 8>(p, stream);
     if (ks <= 12) return launch_scan_mma_inst<SPARSE, 1, 12>(p, stream);
-    return launch_scan_mma_inst<SPARSE, 1, 16>(p, stream);
+    if (ks <= 16) return launch_scan_mma_inst<SPARSE, 1, 16>(p, stream);
+    return launch_scan_mma_inst<SPARSE, 1, 0>(p, stream);
   }
   if (ks <= 4) return launch_scan_mma_inst<SPARSE, 4, 4>(p, stream);
   if (ks <= 8) return launch_scan_mma_inst<SPARSE, 4, 8>(p, stream);
   if (ks <= 12) return launch_scan_mma_inst<SPARSE, 4, 12>(p, stream);
-  return launch_scan_mma_inst<SPARSE, 4, 16>(p, stream);
+  if (ks <= 16) return launch_scan_mma_inst<SPARSE, 4, 16>(p, stream);
+  return launch_scan_mma_inst<SPARSE, 4, 0>(p, stream);
 }
 
 // Launch the (LPR, CH, S) instantiation for this translation unit's (BF16, SPARSE).

@@ -655,11 +655,11 @@ def test_concurrent_searches_on_one_store(store_factory):
     assert not errors, errors[:3]
 
 
-@pytest.mark.parametrize("dim", [8, 24, 100, 128, 200, 384, 500, 512])
+@pytest.mark.parametrize("dim", [8, 24, 100, 128, 200, 384, 500, 512, 520, 768, 1000, 1536])
 @pytest.mark.parametrize("k", [1, 10, 100])
 def test_bf16_scan_on_mma_matches_the_cuda_core_scan_and_the_exact_dot(store_factory, monkeypatch, dim, k):
-    """bf16 rows of up to 512 columns are scored on mma.sync with the fp32 query split into three bf16 terms
-    (scan_mma_topk_kernel).  Products are exact and accumulation is fp32, so the scores must agree with the
+    """bf16 rows are scored on mma.sync with the fp32 query split into three bf16 terms (scan_mma_topk_kernel;
+    query fragments in registers up to dim 512, in shared memory beyond).  Products are exact and accumulation is fp32, so the scores must agree with the
     CUDA-core kernel (PVDB_SCAN_NO_MMA=1) and with the float64 dot product of the stored bf16 rows to ~1e-6
     -- the fp32 tolerance, not the bf16 one -- with deleted rows, a dense and a sparse (prefilter) walk."""
     n = 5003
