@@ -21,12 +21,12 @@ for st in $STAGES; do
       cat gpurun_out/gemm_peaks.json ;;
     ncu_list)
       timeout 600 $SHORT > gpurun_out/plain_short.log 2>&1 &&
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan_topk|batch_topk|finalize_batch|seed_threshold|prepare_queries|merge_topk|exchange_merge|fill_empty" -c 3000 --csv \
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"scan_topk|scan_mma_topk|batch_topk|finalize_batch|seed_threshold|prepare_queries|merge_topk|exchange_merge|fill_empty" -c 3000 --csv \
         --log-file gpurun_out/launches.csv $SHORT > gpurun_out/ncu_list.log 2>&1
       echo "ncu_list rc=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_scan)
       timeout 600 $SHORT > gpurun_out/plain_short2.log 2>&1 &&
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 100 -c 2 \
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"scan_topk|scan_mma_topk" -s 100 -c 2 \
         -f -o gpurun_out/scan_bf16_c5 $SHORT > gpurun_out/ncu_scan.log 2>&1
       echo "ncu_scan rc=$?" | tee -a gpurun_out/summary.txt ;;
     ncu_batch)
