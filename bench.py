@@ -621,7 +621,9 @@ def run_b200(args, world, rank, local_rank):
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm",
-                "kernel": f"scan_topk_kernel<{wl.store_dtype}> (masked GEMV + fused top-k)",
+                "kernel": ("scan_mma_topk_kernel (bf16 rows on mma.sync, fp32 query split into three bf16 terms; masked "
+                           "GEMV + fused top-k)" if wl.store_dtype == "bf16" and not os.environ.get("PVDB_SCAN_NO_MMA")
+                           else f"scan_topk_kernel<{wl.store_dtype}> (masked GEMV + fused top-k)"),
                 "achieved": achieved,
                 "peak": peaks["hbm"],
                 "unit": "GB/s",
