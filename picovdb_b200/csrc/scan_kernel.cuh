@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
 //   * EXACTNESS.  The fp32 query is split into three bf16 terms q = hi + mid + lo (24 mantissa bits: exact)
 //     which ride in columns 0, 1, 2 of the B operand; the other five columns are zero.  Every product
 //     bf16 x bf16 is exact in fp32 and the accumulators are fp32, so a score differs from the CUDA-core
-//     kernel's only by the order of the fp32 additions (~1e-7 for unit vectors; tests hold it to the same
-//     1e-5 / 2e-6 tolerance against the oracle).
+//     kernel's only by the order of the fp32 additions (~1e-7 for unit vectors; the parity tests hold it to the
+//     fp32 tolerance 1e-5 / 2e-6).
 //   * The query fragments stay in REGISTERS (4 per slice: no shared-memory traffic in the loop) for
 //     dim <= 512; wider rows (KS == 0) read them from shared memory, one 16-byte load per slice and thread
 //     (half the shared-memory bytes of the CUDA-core kernel and none of its arithmetic).
