@@ -22,13 +22,18 @@
 //               warp sorts it co-operatively (bitonic network in registers), keeps the best k_sel
 //               and raises the threshold, which both halves share through shared memory.
 //
-// Schedule: a "visit" is (database tile t, query tile qt); visits are numbered tile-major
-// (v = t * q_tiles + qt) and CTA b takes v = b, b + grid, b + 2*grid, ...  At any moment the 148
-// CTAs therefore work on the same handful of database tiles, each of which is fetched from HBM
-// once and then served to the other query tiles from L2 (the first version walked one query tile
-// down a long chunk of database tiles per CTA; CTAs drifted apart and the 10M x 768 case re-read
-// the database 24x from HBM).  A CTA keeps one running (threshold, count, pool) per query tile it
-// meets; at the end it leaves each pool as it is (unsorted, with its count).
+// Schedule: a "visit" is (database tile t, query tile qt); a WORK ITEM is a block of R <= 8 consecutive
+// database tiles for one query tile (pair, with 2-CTA clusters), items are numbered tile-block-major and
+// unit b (CTA or cluster) takes items b, b + units, b + 2 units, ... (VisitSeq below).  At any moment the
+// 148 CTAs therefore work inside a window of a few tile blocks, each database tile is fetched from HBM once
+// and then served to the other query tiles from L2 (the first version walked one query tile down a long
+// chunk of database tiles per CTA; CTAs drifted apart and the 10M x 768 case re-read the database 24x from
+// HBM), and inside an item the epilogue keeps the query tile's thresholds / counters / pool pointers in
+// registers.  A CTA keeps one running (threshold, count, pool) per query tile it meets; at the end it leaves
+// each pool as it is (unsorted, with its count).
+// Both control warps run their loops with ALL lanes and let one elected lane issue (elect_one()): issued
+// from a divergent single-lane branch every tcgen05.mma cost 168 cycles of operand shuffling in SASS and
+// the tensor pipe (128 cycles per 128 x 256 x 16 MMA) was paced by instruction issue.
 // finalize_batch_kernel streams those pools per query through a threshold filter (the best published
 // k_sel-th score is a proven lower bound), sorts what survives, re-scores the best exactly in fp32
 // against the fp32 matrix (tensor-core inputs are rounded to tf32 / bf16; the north star asks for
