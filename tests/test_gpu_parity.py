@@ -692,3 +692,25 @@ def test_bf16_scan_on_mma_matches_the_cuda_core_scan_and_the_exact_dot(store_fac
             kth = np.sort(exact)[::-1][k - 1]
             for r in set(rows[0].tolist()) ^ set(rows_c[0].tolist()):
                 assert abs(exact[r] - kth) <= 4e-6, (r, exact[r], kth)
+
+
+def test_bf16_mma_scan_pages_large_k(store_factory):
+    """k > 128 runs the scan in pages bounded by the previous page's last key; the mma kernel takes the same
+    bound.  Every returned row must be live, scores sorted, and the set equal to the exact top k."""
+    dim, n, k = 200, 4001, 300
+    s = store_factory(dim, keep_f32=False, bf16_mirror=True)
+    s.upsert_range(_gauss(n, dim, 77), 0)
+    dead = np.arange(0, n, 9)
+    s.delete_rows(dead)
+    rows_f64 = s.download().astype(np.float64)
+    q = _gauss(1, dim, 78)
+    qn, _ = O.prepare_queries(q, dim)
+    exact = rows_f64 @ qn[0].astype(np.float64)
+    exact[dead] = -np.inf
+    sc, rows = s.search(q, k)
+    assert np.all(np.diff(sc[0]) <= 0) and len(set(rows[0].tolist())) == k
+    np.testing.assert_allclose(sc[0], exact[rows[0]], rtol=F32_RTOL, atol=F32_ATOL)
+    want = np.argsort(-exact, kind="stable")[:k]
+    kth = exact[want[-1]]
+    for r in set(rows[0].tolist()) ^ set(want.tolist()):
+        assert abs(exact[r] - kth) <= 4e-6
