@@ -1,6 +1,9 @@
 #!/usr/bin/env python
 """Where the batch kernel's warps spend their cycles (needs a library built with
-PVDB_NVCC_EXTRA=-DPVDB_BATCH_STATS).  Usage: python tools/batch_stats.py rows,dim,nq,k,prec[,mirror] ..."""
+PVDB_NVCC_EXTRA=-DPVDB_BATCH_STATS).  CAUTION: every counter is two clock64() reads and one read costs ~100
+cycles on the B200; with ~14 reads per visit the instrumented kernel is 25-40 % slower and small intervals are
+mostly the reads themselves (profiles/round2/README.md, second half, 1.).  Use ncu's source-level sampling
+(--set full --import-source on; tools/gpu_round2b.sh ncu384) for anything finer than per-visit totals.  Usage: python tools/batch_stats.py rows,dim,nq,k,prec[,mirror] ..."""
 import ctypes as C
 import json
 import os
