@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
   const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanMmaWarps;
   const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
   const int row_chunks = p.row_chunks;
+  const bool full_rows = row_chunks == 4 * KR;   // (KS > 0) the row is exactly KS slices wide
 
   // Score the 16 row slots of a warp step (this thread: slots g and g + 8) and feed the warp list.
   auto score_rows = [&](const int64_t (&row)[2], const bool (&on)[2]) {
@@ -439,6 +440,30 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
     const uint4* rp1 = mat + row[1] * row_chunks + t;
     float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
     if constexpr (!QS) {
+      if (full_rows && __all_sync(0xffffffffu, on[0] && on[1])) {
+        // the common case -- every slot holds a live row and the row fills its KS slices exactly: plain loads
+        // with immediate offsets, nothing predicated (the general loop below spends ~4 instructions per load
+        // on predicates and zero fills)
+#pragma unroll
+        for (int ks0 = 0; ks0 < KS; ks0 += 4) {
+          uint4 v0[4], v1[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (ks0 + i < KS) {
+              v0[i] = ldg_stream(rp0 + (ks0 + i) * 4);
+              v1[i] = ldg_stream(rp1 + (ks0 + i) * 4);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int ks = ks0 + i;
+            if (ks < KS) {
+              mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, bq[ks][0], bq[ks][1]);
+              mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, bq[ks][2], bq[ks][3]);
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int ks0 = 0; ks0 < KS; ks0 += 4) {
         if (ks0 * 4 >= row_chunks) break;   // (warp-uniform) slices past the row
@@ -458,6 +483,7 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
             mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, bq[ks][2], bq[ks][3]);
           }
         }
+      }
       }
     } else {
       for (int ks0 = 0; ks0 < n_slices; ks0 += 4) {
