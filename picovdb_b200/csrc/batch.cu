@@ -81,9 +81,10 @@ constexpr int kSlackTF32 = 32;
 constexpr int kSlackBF16 = 54;
 constexpr int kSlackLargeK = 60;
 constexpr int kSampleFraction = 16; // the sample pass covers 1/16 of the database tiles
-// The pair (cta_group::2) variant is validated (all batch tests pass with PVDB_BATCH_PAIR=1) but measured
-// SLOWER on the B200 than 2-CTA clusters with cta_group::1 MMAs + TMA multicast (C3: 140 vs 105 ms,
-// C5 batch: 34.9 vs 32.4 ms), so it stays opt-in.
+// The pair (cta_group::2) variant is validated (all batch tests pass with PVDB_BATCH_PAIR=1).  It measured 15 %
+// slower than 2-CTA clusters with cta_group::1 MMAs + TMA multicast until its accumulator hand-back stopped
+// issuing a cluster-wide memory barrier per visit (mbar_arrive_cluster); since then it is within +-2 % of
+// the default (12.5M x 384 bf16: 30.6-31.3 vs 30.0-30.4 ms), so it stays opt-in.
 constexpr bool kPairDefault = false;
 constexpr int kClusterDefault = 2;  // CTAs per cluster sharing a database tile; 4 and 8 work but measured 3 % / 10 % slower
 constexpr int kMaxQTiles = 32;      // query tiles per launch (4096 queries); larger batches are split
@@ -236,8 +237,13 @@ __device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar, uint16_t mask)
                ::"r"(bar), "h"(mask)
                : "memory");
 }
+// Arrival on the PEER CTA's barrier (pair variant: the epilogue hands an accumulator back to the leader's MMA
+// warp).  Relaxed: what the arrival orders are this warp's tcgen05.ld reads, which have completed
+// (tcgen05.wait::ld) and are fenced by tcgen05.fence::before_thread_sync; a .release.cluster arrival compiled to
+// a cluster-wide memory barrier that waited for the warp's outstanding pool stores on every visit (13 % of the
+// pair variant's stall samples).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <bool BF16>
 __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
