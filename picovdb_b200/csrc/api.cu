@@ -35,9 +35,11 @@ static int fill_empty(float* d_scores, int64_t* d_rows, int64_t n, cudaStream_t 
 // the scan kernel itself.
 // ex (optional, k <= kFusedK only): every launch exchanges its list with the peer GPUs inside the
 // kernel and writes the merged, final top k (one exchange sequence number per query).
+// h_sel (optional, host): serve only the queries h_sel[0 .. nq) of the arrays (the guard's flagged queries); every
+// pointer still addresses the WHOLE query / result arrays.
 static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float* d_raw, int64_t nq, int k,
                        const uint32_t* d_pref, float* d_out_scores, int64_t* d_out_rows, cudaStream_t st,
-                       pvdb_exchange* ex = nullptr) {
+                       pvdb_exchange* ex = nullptr, const int* h_sel = nullptr) {
   const int grid = scan_grid_blocks();
   const size_t list_bytes = static_cast<size_t>(grid) * kFusedK * sizeof(uint64_t);
   PVDB_TRY(s->d_partial.ensure(list_bytes + 64));
@@ -58,20 +60,45 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
   p.ticket = reinterpret_cast<unsigned int*>(ctrl);
   p.next_upper = reinterpret_cast<uint64_t*>(ctrl + 8);
   p.row_base = s->row_base;
-  for (int64_t q = 0; q < nq; ++q) {
-    p.query = d_qn ? d_qn + q * s->ldq : nullptr;
-    p.raw_query = d_qn ? nullptr : d_raw + q * s->dim;
-    p.dim = s->dim;
+  p.dim = s->dim;
+  p.nq = 1;
+  // Several queries of one call share a pass over the matrix where the kernels allow it (k <= 32, no fused
+  // exchange: scan_kernel.cuh, "several queries per pass"); a lone query, a remainder of one, large k and
+  // exchanging launches take the single-query kernels.
+  const int width = (ex == nullptr && nq > 1) ? scan_multi_width(bf16, s->ldq, k) : 1;
+  int64_t q = 0;
+  bool first = true;
+  auto sel = [&](int64_t i) -> int64_t { return h_sel ? h_sel[i] : i; };
+  for (; width > 1 && nq - q >= 2; q += width) {
+    p.nq = static_cast<int>(std::min<int64_t>(width, nq - q));
+    for (int j = 0; j < 4; ++j) p.qsel[j] = j < p.nq ? sel(q + j) : 0;
+    p.query = d_qn;
+    p.raw_query = d_qn ? nullptr : d_raw;
+    p.k = k;
+    p.upper = nullptr;
+    p.out_scores = d_out_scores;
+    p.out_rows = d_out_rows;
+    p.xv = ExchangeView{};
+    p.pdl = !first && !no_pdl;
+    first = false;
+    PVDB_TRY(launch_scan_multi(p, bf16, st));
+  }
+  p.nq = 1;
+  for (; q < nq; ++q) {
+    const int64_t qi = sel(q);
+    p.query = d_qn ? d_qn + qi * s->ldq : nullptr;
+    p.raw_query = d_qn ? nullptr : d_raw + qi * s->dim;
     for (int k0 = 0; k0 < k; k0 += kFusedK) {
       p.k = std::min(kFusedK, k - k0);
       p.upper = (k0 == 0) ? nullptr : p.next_upper;
-      p.out_scores = d_out_scores + q * k + k0;
-      p.out_rows = d_out_rows + q * k + k0;
+      p.out_scores = d_out_scores + qi * k + k0;
+      p.out_rows = d_out_rows + qi * k + k0;
       p.xv = ExchangeView{};
       if (ex != nullptr) p.xv = ex->next_view();
       // second and later launches of this call: the previous operation on the stream is a scan whose
       // inputs were complete before it started (PVDB_SCAN_NO_PDL=1 switches the overlap off)
-      p.pdl = (q > 0 || k0 > 0) && !no_pdl;
+      p.pdl = (!first || k0 > 0) && !no_pdl;
+      first = false;
       PVDB_TRY(launch_scan(p, bf16, st));
     }
   }
@@ -200,16 +227,15 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
     if (n_flag > 0)
     PVDB_CUDA(cudaMemcpyAsync(h + 4, d_flag_list, static_cast<size_t>(n_flag) * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (n_flag > 0) PVDB_CUDA(cudaStreamSynchronize(st));
-    for (int64_t i = 0; i < n_flag; ++i) {
-      const int64_t q = h[4 + i];
-      if (q < 0 || q >= nq) return fail(PVDB_ERR_CUDA, "guard: corrupt flag list");
-      // exactly the call a lone query takes: raw query normalised inside the scan kernel
+    for (int64_t i = 0; i < n_flag; ++i)
+      if (h[4 + i] < 0 || h[4 + i] >= nq) return fail(PVDB_ERR_CUDA, "guard: corrupt flag list");
+    // the arithmetic a lone query gets (raw query normalised inside the scan kernel), several flagged queries
+    // per pass over the matrix where the scan kernels allow it
+    if (n_flag > 0) {
       if (normalised)
-        PVDB_TRY(search_scan(s, !has_f32, d_qn + q * s->ldq, nullptr, 1, k, d_pref, d_out_scores + q * k,
-                             d_out_rows + q * k, st));
+        PVDB_TRY(search_scan(s, !has_f32, d_qn, nullptr, n_flag, k, d_pref, d_out_scores, d_out_rows, st, nullptr, h + 4));
       else
-        PVDB_TRY(search_scan(s, !has_f32, nullptr, d_queries + q * s->dim, 1, k, d_pref, d_out_scores + q * k,
-                             d_out_rows + q * k, st));
+        PVDB_TRY(search_scan(s, !has_f32, nullptr, d_queries, n_flag, k, d_pref, d_out_scores, d_out_rows, st, nullptr, h + 4));
     }
     if (ex != nullptr) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
     return PVDB_OK;

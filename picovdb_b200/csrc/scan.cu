@@ -32,12 +32,19 @@ int launch_scan_mma_variant(const ScanParams& p, cudaStream_t stream);
 extern template int launch_scan_mma_variant<false>(const ScanParams&, cudaStream_t);
 extern template int launch_scan_mma_variant<true>(const ScanParams&, cudaStream_t);
 
-int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
-  if (p.k < 1 || p.k > kFusedK) return fail(PVDB_ERR_INVALID, "scan: k=%d outside [1, %d]", p.k, kFusedK);
-  if (p.query_floats > 16384) return fail(PVDB_ERR_UNSUPPORTED, "scan: dim > 16384 not supported");
-  // lanes per row: the widest of {32,16,8} that divides the row's 16-byte chunk count (else the
-  // widest that does not exceed it), then the smallest unroll in {1,2,4,8} covering the row.
-  const int rc = p.row_chunks;
+// defined in scan_inst_f32_multi_*.cu / scan_inst_bf16_mma_multi_*.cu
+template <bool SPARSE>
+int launch_scan_multi_variant(const ScanParams& p, int lpr, int ch, cudaStream_t stream);
+extern template int launch_scan_multi_variant<false>(const ScanParams&, int, int, cudaStream_t);
+extern template int launch_scan_multi_variant<true>(const ScanParams&, int, int, cudaStream_t);
+template <bool SPARSE>
+int launch_scan_mma_multi_variant(const ScanParams& p, cudaStream_t stream);
+extern template int launch_scan_mma_multi_variant<false>(const ScanParams&, cudaStream_t);
+extern template int launch_scan_mma_multi_variant<true>(const ScanParams&, cudaStream_t);
+
+// lanes per row: the widest of {32,16,8} that divides the row's 16-byte chunk count (else the
+// widest that does not exceed it), then the smallest unroll in {1,2,4,8} covering the row.
+static void scan_row_shape(int rc, int* lpr_out, int* ch_out) {
   int lpr = 8;
   if (rc % 32 == 0) lpr = 32;
   else if (rc % 16 == 0) lpr = 16;
@@ -45,7 +52,47 @@ int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
   else if (rc >= 32) lpr = 32;
   else if (rc >= 16) lpr = 16;
   const int per_lane = (rc + lpr - 1) / lpr;
-  const int ch = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
+  *lpr_out = lpr;
+  *ch_out = per_lane <= 1 ? 1 : per_lane <= 2 ? 2 : per_lane <= 4 ? 4 : 8;
+}
+
+// Several queries per pass (scan_kernel.cuh): 4 over fp32 rows, 2 over bf16 rows on mma.sync; k <= 32; the
+// queries of one launch must fit shared memory next to the lists.  PVDB_SCAN_NO_MULTI=1 switches it off.
+int scan_multi_width(bool is_bf16, int query_floats, int k) {
+  const bool off = getenv("PVDB_SCAN_NO_MULTI") != nullptr;
+  const bool no_mma = getenv("PVDB_SCAN_NO_MMA") != nullptr;
+  if (off || k < 1 || k > 32) return 1;
+  if (is_bf16 && no_mma) return 1;   // the CUDA-core bf16 kernel has no several-queries form
+  const int nq = is_bf16 ? 2 : 4;
+  // fp32: nq queries + 16 warps x nq lists; bf16 (wide rows): + 3 nq fragment parts of query_floats / 2 words
+  const size_t smem = static_cast<size_t>(nq) * query_floats * sizeof(float) + static_cast<size_t>(nq) * 16 * k * 8 +
+                      (is_bf16 ? static_cast<size_t>(3 * nq) * (query_floats / 2 + 16) * sizeof(uint32_t) : 0);
+  return smem <= 160 * 1024 ? nq : 1;
+}
+
+int launch_scan_multi(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
+  const int width = scan_multi_width(is_bf16, p.query_floats, p.k);
+  if (p.nq < 1 || p.nq > width || p.upper != nullptr || p.xv.world > 0)
+    return fail(PVDB_ERR_INVALID, "scan: %d queries per pass not available here (width %d, k=%d)", p.nq, width, p.k);
+  const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
+  if (is_bf16) return sparse ? launch_scan_mma_multi_variant<true>(p, stream) : launch_scan_mma_multi_variant<false>(p, stream);
+  int lpr, ch;
+  scan_row_shape(p.row_chunks, &lpr, &ch);
+  // Every 16-byte chunk of a row meets NQ query chunks from shared memory; with R = 16 / CH rows in flight per
+  // lane group one query read serves R rows.  CH = 8 with 8 loads in flight (R = 1, what a lone query takes on
+  // wide rows) spent 4 LDS.128 per loaded chunk -- ~80 % of the shared-memory pipe at HBM speed; measured
+  // 3.4 TB/s on 100k x 1024 -- so the several-queries kernels cap CH at 4 (R >= 4; CH = 2 spills).
+  int ch_cap = 4;
+  if (const char* e = getenv("PVDB_SCAN_MULTI_CH")) ch_cap = atoi(e);
+  ch = std::min(ch, std::max(1, ch_cap));
+  return sparse ? launch_scan_multi_variant<true>(p, lpr, ch, stream) : launch_scan_multi_variant<false>(p, lpr, ch, stream);
+}
+
+int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream) {
+  if (p.k < 1 || p.k > kFusedK) return fail(PVDB_ERR_INVALID, "scan: k=%d outside [1, %d]", p.k, kFusedK);
+  if (p.query_floats > 16384) return fail(PVDB_ERR_UNSUPPORTED, "scan: dim > 16384 not supported");
+  int lpr, ch;
+  scan_row_shape(p.row_chunks, &lpr, &ch);
   // a prefilter usually leaves a small fraction of the rows: walk the bitmap, not the rows
   const bool sparse = p.prefilter != nullptr && getenv("PVDB_SCAN_NO_SPARSE") == nullptr;
   // bf16 rows: dot products on mma.sync (fewer instructions per byte: the chip sustains more of its HBM

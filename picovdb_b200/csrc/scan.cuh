@@ -29,6 +29,10 @@ struct ScanParams {
   int dim;
   int query_floats;          // padded query length
   int k;                     // 1 .. kFusedK for this pass
+  int nq;                    // queries this launch serves: 1, or up to NQ in the several-queries-per-pass kernels
+                             // (query j of the launch is query qsel[j] of query / raw_query and writes result
+                             // row qsel[j] of out_scores / out_rows)
+  int64_t qsel[4];
   const uint64_t* upper;     // only keys strictly below *upper qualify (paging); NULL = no bound
   uint64_t* partial;         // [gridDim.x][k] per-block lists
   unsigned int* ticket;      // last-block-done counter (self-resetting)
@@ -46,6 +50,11 @@ struct ScanParams {
 
 // Launch one scan pass on `stream`.  `is_bf16` selects the mirror layout.
 int launch_scan(const ScanParams& p, bool is_bf16, cudaStream_t stream);
+// Several queries per pass over the matrix (scan_kernel.cuh, "several queries per pass"): how many queries one
+// launch can take for this store layout and k (1 = only the single-query kernels apply), and the launch itself
+// (p.nq in [2, scan_multi_width]; no paging bound, no exchange).
+int scan_multi_width(bool is_bf16, int query_floats, int k);
+int launch_scan_multi(const ScanParams& p, bool is_bf16, cudaStream_t stream);
 int scan_grid_blocks();
 
 // Query preparation (picovdb/pico_vdb.py:584-591): L2-normalise each query in fp32, zero -> e0,

@@ -184,6 +184,283 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
   }
 }
 
+// ---------------------------------------------------------------------------- several queries per pass
+// A batch that must be answered EXACTLY (precision "f32", or the queries the tensor-core guard could not prove)
+// used to cost one pass over the matrix per query.  The scan is HBM bound with arithmetic to spare, so the
+// kernels below score NQ queries against every row they load: fp32 rows x 4 queries on the CUDA cores
+// (16 FMA per 16-byte chunk instead of 4), bf16 rows x 2 queries on mma.sync (the second query's three terms
+// fill B columns the single-query form leaves zero).  Per query the arithmetic -- normalisation, products,
+// order of the additions, key order -- is the single-query kernel's, so a query gets the same bits alone and
+// in a group.  k <= 32 (one 32-key slot per list), no paging bound, no fused exchange: callers fall back to
+// the single-query kernels outside that.
+//
+// Prologue: p.nq (<= NQ) consecutive queries go to shared memory, query q at sq[q * query_floats ...]; the
+// slots of absent queries are zero and never produce candidates.
+template <int NQ>
+__device__ __forceinline__ void scan_prologue_multi(const ScanParams& p, float* sq) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int qf = p.query_floats;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (p.raw_query != nullptr) {
+    // the single-query prologue per query: lane-strided fp32 partial sums of ONE warp, fp64 butterfly
+    __shared__ float s_nrm[NQ];
+    for (int i = tid; i < NQ * qf; i += static_cast<int>(blockDim.x)) {
+      const int q = i / qf, c = i - q * qf;
+      sq[i] = (q < p.nq && c < p.dim) ? p.raw_query[p.qsel[q] * p.dim + c] : 0.f;
+    }
+    __syncthreads();
+    if (warp < NQ) {
+      const float* s = sq + warp * qf;
+      float ss = 0.f;
+      for (int c = lane; c < p.dim; c += 32) {
+        const float x = s[c];
+        ss = fmaf(x, x, ss);
+      }
+      double d = static_cast<double>(ss);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (lane == 0) s_nrm[warp] = static_cast<float>(sqrt(d));
+    }
+    __syncthreads();
+    for (int i = tid; i < NQ * qf; i += static_cast<int>(blockDim.x)) {
+      const int q = i / qf, c = i - q * qf;
+      const float nrm = s_nrm[q];
+      const float x = sq[i];
+      sq[i] = (q >= p.nq) ? 0.f : ((nrm == 0.f) ? (c == 0 ? 1.f : 0.f) : __fdiv_rn(x, nrm));
+    }
+  } else {
+    for (int i = tid; i < NQ * qf; i += static_cast<int>(blockDim.x)) {
+      const int q = i / qf, c = i - q * qf;
+      sq[i] = (q < p.nq) ? p.query[p.qsel[q] * qf + c] : 0.f;
+    }
+  }
+  __syncthreads();
+}
+
+// Finish: per-query block merge (warp q folds every warp's list of query q), one ticket per block, and in the
+// last block the warps split the per-block lists by query (warp w: query w % NQ, every (n_warps / NQ)-th
+// block list) before one warp per query folds those and writes the result rows of its query.
+template <int NQ>
+__device__ __forceinline__ void scan_finish_multi(const ScanParams& p, WarpList<1> (&L)[NQ], uint64_t* slist) {
+  __shared__ unsigned s_is_last;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int k = p.k;
+  const int n_warps = static_cast<int>(blockDim.x >> 5);   // a multiple of NQ
+  const int grid = static_cast<int>(gridDim.x);
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) store_list(L[q], slist + (q * n_warps + warp) * k, k, lane);
+  __syncthreads();
+  // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  WarpList<1> M;
+  uint64_t thr = 0ull;
+  M.clear();
+  if (warp < NQ) {
+    for (int w2 = 0; w2 < n_warps; ++w2) merge_list<false, 1>(M, thr, slist + (warp * n_warps + w2) * k, k, k, lane);
+    store_list(M, p.partial + (static_cast<size_t>(blockIdx.x) * NQ + warp) * k, k, lane);
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(p.ticket, 1u);
+    s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_is_last == 0u) return;
+
+  // ---- last block
+  __threadfence();
+  const int q = warp % NQ, part = warp / NQ, parts = n_warps / NQ;
+  M.clear();
+  thr = 0ull;
+  for (int b0 = part; b0 < grid; b0 += parts * 8) {
+    uint64_t head[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int b = b0 + j * parts;
+      head[j] = (b < grid && lane < k) ? load_key<true>(p.partial + (static_cast<size_t>(b) * NQ + q) * k + lane) : 0ull;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
+      while (m) {
+        const int srcl = __ffs(m) - 1;
+        m &= m - 1;
+        const uint64_t x = shfl_u64(head[j], srcl);
+        if (x > thr) {
+          M.insert(x, lane);
+          thr = M.get(k - 1);
+        }
+      }
+    }
+  }
+  store_list(M, slist + (q * parts + part) * k, k, lane);   // (every warp passed the block merge's reads: two barriers ago)
+  __syncthreads();
+  if (warp < NQ) {
+    M.clear();
+    thr = 0ull;
+    for (int p2 = 0; p2 < parts; ++p2) merge_list<false, 1>(M, thr, slist + (warp * parts + p2) * k, k, k, lane);
+    if (warp < p.nq && lane < k) {
+      const uint64_t key = M.slot[0];
+      const int64_t o = p.qsel[warp] * k + lane;
+      p.out_scores[o] = key ? key_score(key) : -INFINITY;
+      p.out_rows[o] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
+    }
+  }
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+constexpr int kScanMultiThreads = 512;  // x 1 block per SM: 128 registers per thread (NQ accumulators, lists, thresholds)
+constexpr int kScanMultiWarps = kScanMultiThreads / 32;
+#ifndef PVDB_SCAN_MULTI_LOADS
+#define PVDB_SCAN_MULTI_LOADS 16
+#endif
+constexpr int kScanMultiLoads = PVDB_SCAN_MULTI_LOADS;   // 16-byte loads a lane keeps in flight per step: with half the
+                                                         // warps of the single-query kernel per SM, twice its 8
+
+// fp32 rows x NQ queries on the CUDA cores; the walk and the per-lane arithmetic are scan_topk_kernel's.
+template <int LPR, int CH, bool SPARSE, int NQ>
+__global__ void __launch_bounds__(kScanMultiThreads, 1) scan_multi_topk_kernel(const ScanParams p) {
+  constexpr int G = 32 / LPR;  // row groups per warp
+  constexpr int R = (kScanMultiLoads / CH) * G <= 32 ? kScanMultiLoads / CH : 32 / G;   // rows in flight per group
+  constexpr int RPW = G * R;   // rows per warp step: one bitmap word covers it
+  static_assert(kScanMultiWarps % NQ == 0, "the last block splits its warps evenly over the queries");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sq = reinterpret_cast<float*>(smem_raw);
+  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(NQ) * p.query_floats * sizeof(float));
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int sub = lane % LPR;
+  const int gi = lane / LPR;
+  const int k = p.k;
+  const int nq = p.nq;
+
+  scan_prologue_multi<NQ>(p, sq);
+  const float4* sq4 = reinterpret_cast<const float4*>(sq);
+  const int q_chunks = p.query_floats / 4;   // float4 per query
+
+  WarpList<1> L[NQ];
+  uint64_t thr[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    L[q].clear();
+    thr[q] = 0ull;
+  }
+
+  const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanMultiWarps;
+  const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
+  const int row_chunks = p.row_chunks;
+
+  auto score_rows = [&](const int64_t (&row)[R], const bool (&on)[R]) {
+    float acc[NQ][R];
+    const uint4* rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      rp[r] = mat + row[r] * row_chunks;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[q][r] = 0.f;
+    }
+    for (int c0 = 0; c0 < row_chunks; c0 += LPR * CH) {
+      uint4 v[R][CH];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int idx = c0 + i * LPR + sub;
+          v[r][i] = (on[r] && idx < row_chunks) ? ldg_stream(rp[r] + idx) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int idx = c0 + i * LPR + sub;
+        if (idx < row_chunks) {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const float4 qv = sq4[q * q_chunks + idx];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[q][r] = dot_chunk_f32(v[r][i], qv, acc[q][r]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) acc[q][r] += __shfl_xor_sync(0xffffffffu, acc[q][r], o);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (q >= nq) break;   // (warp-uniform) the last launch of a call may carry fewer than NQ queries
+        const float sc = acc[q][r];
+        const uint64_t key = (on[r] && sc == sc) ? make_key(sc, static_cast<uint32_t>(row[r])) : 0ull;
+        unsigned m = __ballot_sync(0xffffffffu, sub == 0 && key > thr[q]);
+        while (m) {
+          const int srcl = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t x = shfl_u64(key, srcl);
+          if (x > thr[q]) {
+            L[q].insert(x, lane);
+            thr[q] = L[q].get(k - 1);
+          }
+        }
+      }
+    }
+  };
+
+  if constexpr (!SPARSE) {
+    const int64_t n_steps = (p.n_rows + RPW - 1) / RPW;
+    for (int64_t step = static_cast<int64_t>(blockIdx.x) * kScanMultiWarps + warp; step < n_steps; step += total_warps) {
+      const int64_t base = step * RPW;
+      uint32_t w = __ldg(p.active + (base >> 5));
+      if (p.prefilter) w &= __ldg(p.prefilter + (base >> 5));
+      w >>= (base & 31);
+      if constexpr (RPW < 32) w &= (1u << RPW) - 1u;
+      if (w == 0u) continue;
+      int64_t row[R];
+      bool on[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int local = r * G + gi;
+        on[r] = (w >> local) & 1u;
+        row[r] = base + local;
+      }
+      score_rows(row, on);
+    }
+  } else {
+    const int64_t n_words = (p.n_rows + 31) >> 5;
+    for (int64_t wi = static_cast<int64_t>(blockIdx.x) * kScanMultiWarps + warp; wi < n_words; wi += total_warps) {
+      uint32_t w = __ldg(p.active + wi);
+      if (w != 0u && p.prefilter) w &= __ldg(p.prefilter + wi);
+      while (w != 0u) {
+        int64_t row[R];
+        bool on[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const unsigned bit = __fns(w, 0, r * G + gi + 1);
+          on[r] = bit < 32u;
+          row[r] = (wi << 5) + (on[r] ? bit : 0u);
+        }
+        score_rows(row, on);
+        if constexpr (RPW >= 32) {
+          w = 0u;
+        } else {
+          const unsigned last = __fns(w, 0, RPW);
+          w = (last < 31u) ? (w & (0xffffffffu << (last + 1))) : 0u;
+        }
+      }
+    }
+  }
+  scan_finish_multi<NQ>(p, L, slist);
+}
+
 // LPR lanes cooperate on one row; each lane keeps CH 16-byte loads of R rows in flight
 // (CH * R == 8 -> eight independent 128-bit loads per lane per step).
 // S: 32-key slots of the per-warp list (1 for k <= 32 -- cheaper inserts and merges, fewer registers;
@@ -372,17 +649,21 @@ __device__ __forceinline__ uint32_t bf16_split_part(float x, int part) {
 constexpr int kScanMmaThreads = 256;   // x 2 blocks per SM: up to 128 registers per thread (48-64 hold the query fragments)
 constexpr int kScanMmaWarps = kScanMmaThreads / 32;
 
-template <bool SPARSE, int S, int KS>
+// NQ: queries per pass -- 1, or 2 (S == 1): the second query's three terms ride in B columns 3-5, which the
+// single-query form leaves zero, so two queries cost the instructions of one ("several queries per pass" below).
+template <bool SPARSE, int S, int KS, int NQ>
 __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_topk_kernel(const ScanParams p) {
+  static_assert(NQ == 1 || (NQ == 2 && S == 1), "two queries per pass keep one 32-key slot per list");
   constexpr int RPW = 16;  // rows per warp step (the M of the MMA)
   constexpr bool QS = KS == 0;   // query fragments in shared memory
   constexpr int KR = QS ? 1 : KS;
+  constexpr int NP = 3 * NQ;     // B columns in use: part (g % 3) of query (g / 3)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sq = reinterpret_cast<float*>(smem_raw);
-  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(p.query_floats) * sizeof(float));
-  // QS: [3 parts][n_slices * 16] packed bf16 pairs behind the lists (8 warps x k keys x 8 bytes: 16-byte aligned)
+  uint64_t* slist = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(NQ) * p.query_floats * sizeof(float));
+  // QS: [NP parts][n_slices * 16] packed bf16 pairs behind the lists (8 warps x k keys x 8 bytes: 16-byte aligned)
   static_assert((kScanMmaWarps * sizeof(uint64_t)) % 16 == 0, "the fragment words must stay 16-byte aligned");
-  uint32_t* sfrag = reinterpret_cast<uint32_t*>(slist + static_cast<size_t>(kScanMmaWarps) * p.k);
+  uint32_t* sfrag = reinterpret_cast<uint32_t*>(slist + static_cast<size_t>(NQ) * kScanMmaWarps * p.k);
   const int n_slices = (p.row_chunks + 3) / 4;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -390,10 +671,12 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
   const int t = lane & 3;    // which 8 columns of every 32-column slice
   const int k = p.k;
 
-  scan_prologue(p, sq);
+  if constexpr (NQ == 1) scan_prologue(p, sq);
+  else scan_prologue_multi<NQ>(p, sq);
 
   // query fragments: slice ks, this thread's columns c0 = 32 ks + 8 t ... c0 + 7 as four bf16 pairs of
-  // part g of the split (threads with g >= 3 feed the unused B columns: zeros)
+  // part g % 3 of the split of query g / 3 (threads with g >= NP feed the unused B columns: zeros)
+  const float* sqg = sq + (g < NP ? g / 3 : 0) * p.query_floats;
   uint32_t bq[KR][4];
   if constexpr (!QS) {
 #pragma unroll
@@ -402,32 +685,37 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
       for (int j = 0; j < 4; ++j) {
         const int c = ks * 32 + t * 8 + 2 * j;
         uint32_t w = 0u;
-        if (g < 3 && c < p.query_floats) {
-          const float x0 = sq[c];
-          const float x1 = (c + 1 < p.query_floats) ? sq[c + 1] : 0.f;
-          w = bf16_split_part(x0, g) | (bf16_split_part(x1, g) << 16);
+        if (g < NP && c < p.query_floats) {
+          const float x0 = sqg[c];
+          const float x1 = (c + 1 < p.query_floats) ? sqg[c + 1] : 0.f;
+          w = bf16_split_part(x0, g % 3) | (bf16_split_part(x1, g % 3) << 16);
         }
         bq[ks][j] = w;
       }
     }
   } else {
-    // word i of part q covers columns 2 i, 2 i + 1
+    // word i of part pt covers columns 2 i, 2 i + 1 of query pt / 3
     const int words = n_slices * 16;
-    for (int i = threadIdx.x; i < 3 * words; i += kScanMmaThreads) {
+    for (int i = threadIdx.x; i < NP * words; i += kScanMmaThreads) {
       const int part = i / words, c = 2 * (i - part * words);
-      const float x0 = c < p.query_floats ? sq[c] : 0.f;
-      const float x1 = c + 1 < p.query_floats ? sq[c + 1] : 0.f;
-      sfrag[i] = bf16_split_part(x0, part) | (bf16_split_part(x1, part) << 16);
+      const float* sqp = sq + (part / 3) * p.query_floats;
+      const float x0 = c < p.query_floats ? sqp[c] : 0.f;
+      const float x1 = c + 1 < p.query_floats ? sqp[c + 1] : 0.f;
+      sfrag[i] = bf16_split_part(x0, part % 3) | (bf16_split_part(x1, part % 3) << 16);
     }
     __syncthreads();
   }
-  // this thread's fragment words of slice ks sit at sfrag4[ks * 4] (threads with g >= 3 feed zero columns)
-  const uint4* sfrag4 = reinterpret_cast<const uint4*>(sfrag + (g < 3 ? g : 0) * n_slices * 16) + t;
+  // this thread's fragment words of slice ks sit at sfrag4[ks * 4] (threads with g >= NP feed zero columns)
+  const uint4* sfrag4 = reinterpret_cast<const uint4*>(sfrag + (g < NP ? g : 0) * n_slices * 16) + t;
 
   const uint64_t upper = p.upper ? *p.upper : ~0ull;
-  WarpList<S> L;
-  L.clear();
-  uint64_t thr = 0ull;
+  WarpList<S> L[NQ];
+  uint64_t thr[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    L[q].clear();
+    thr[q] = 0ull;
+  }
 
   const int64_t total_warps = static_cast<int64_t>(gridDim.x) * kScanMmaWarps;
   const uint4* mat = reinterpret_cast<const uint4*>(p.matrix);
@@ -499,7 +787,7 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
         for (int i = 0; i < 4; ++i) {
           const int ks = ks0 + i;
           if (ks < n_slices) {
-            const uint4 f = g < 3 ? sfrag4[ks * 4] : make_uint4(0u, 0u, 0u, 0u);
+            const uint4 f = g < NP ? sfrag4[ks * 4] : make_uint4(0u, 0u, 0u, 0u);
             mma_bf16_16816(ca, v0[i].x, v1[i].x, v0[i].y, v1[i].y, f.x, f.y);
             mma_bf16_16816(cb, v0[i].z, v1[i].z, v0[i].w, v1[i].w, f.z, f.w);
           }
@@ -509,18 +797,31 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
     // thread t == 0 holds (hi, mid) of rows g / g + 8 in c[0..1] / c[2..3]; thread t == 1 holds lo in c[0] / c[2]
     const float c0 = ca[0] + cb[0], c1 = ca[1] + cb[1], c2 = ca[2] + cb[2], c3 = ca[3] + cb[3];
     const float lo0 = __shfl_down_sync(0xffffffffu, c0, 1), lo1 = __shfl_down_sync(0xffffffffu, c2, 1);
-    const float sc[2] = {(lo0 + c1) + c0, (lo1 + c3) + c2};
+    float sc[2] = {(lo0 + c1) + c0, (lo1 + c3) + c2};
+    if constexpr (NQ == 2) {
+      // second query: hi in c[1] / c[3] of thread t == 1, (mid, lo) in c[0..1] / c[2..3] of thread t == 2; the
+      // same (lo + mid) + hi as above, so a query scores to the same bits in either place
+      const float d1 = __shfl_down_sync(0xffffffffu, c1, 1), d3 = __shfl_down_sync(0xffffffffu, c3, 1);
+      if (t == 1) {
+        sc[0] = (d1 + lo0) + c1;
+        sc[1] = (d3 + lo1) + c3;
+      }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const uint64_t key = (on[r] && sc[r] == sc[r]) ? make_key(sc[r], static_cast<uint32_t>(row[r])) : 0ull;
-      unsigned m = __ballot_sync(0xffffffffu, t == 0 && key > thr && key < upper);
-      while (m) {
-        const int srcl = __ffs(m) - 1;
-        m &= m - 1;
-        const uint64_t x = shfl_u64(key, srcl);
-        if (x > thr) {
-          L.insert(x, lane);
-          thr = L.get(k - 1);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        if (NQ > 1 && q >= p.nq) break;   // (warp-uniform) the last launch of a call may carry one query
+        unsigned m = __ballot_sync(0xffffffffu, t == q && key > thr[q] && key < upper);
+        while (m) {
+          const int srcl = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t x = shfl_u64(key, srcl);
+          if (x > thr[q]) {
+            L[q].insert(x, lane);
+            thr[q] = L[q].get(k - 1);
+          }
         }
       }
     }
@@ -556,15 +857,16 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
       }
     }
   }
-  scan_finish<S>(p, L, thr, slist);
+  if constexpr (NQ == 1) scan_finish<S>(p, L[0], thr[0], slist);
+  else scan_finish_multi<NQ>(p, L, slist);
 }
 
-template <bool SPARSE, int S, int KS>
+template <bool SPARSE, int S, int KS, int NQ = 1>
 static int launch_scan_mma_inst(const ScanParams& p, cudaStream_t stream) {
-  size_t smem = static_cast<size_t>(p.query_floats) * sizeof(float) +
-                static_cast<size_t>(kScanMmaWarps) * p.k * sizeof(uint64_t);
-  if (KS == 0) smem += static_cast<size_t>(3) * ((p.row_chunks + 3) / 4) * 16 * sizeof(uint32_t);
-  auto kern = scan_mma_topk_kernel<SPARSE, S, KS>;
+  size_t smem = static_cast<size_t>(NQ) * p.query_floats * sizeof(float) +
+                static_cast<size_t>(NQ) * kScanMmaWarps * p.k * sizeof(uint64_t);
+  if (KS == 0) smem += static_cast<size_t>(3 * NQ) * ((p.row_chunks + 3) / 4) * 16 * sizeof(uint32_t);
+  auto kern = scan_mma_topk_kernel<SPARSE, S, KS, NQ>;
   if (smem > 48 * 1024)
     PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   if (p.pdl) {
@@ -651,6 +953,67 @@ int launch_scan_variant(const ScanParams& p, int lpr, int ch, cudaStream_t strea
   if (lpr == 32) return launch_scan_ch<BF16, SPARSE, 32, 4>(p, ch, stream);
   if (lpr == 16) return launch_scan_ch<BF16, SPARSE, 16, 4>(p, ch, stream);
   return launch_scan_ch<BF16, SPARSE, 8, 4>(p, ch, stream);
+}
+
+
+// ---------------------------------------------------------------------------- several queries per pass: launchers
+constexpr int kScanMultiF32 = 4;    // queries per pass, fp32 rows
+constexpr int kScanMultiBf16 = 2;   // queries per pass, bf16 rows (mma form)
+
+template <typename Kern>
+static int launch_scan_multi_kernel(Kern kern, const ScanParams& p, int blocks, int threads, size_t smem, cudaStream_t stream) {
+  if (smem > 48 * 1024)
+    PVDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  PVDB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  PVDB_LAUNCH_CHECK();
+  return PVDB_OK;
+}
+
+template <bool SPARSE, int LPR>
+static int launch_scan_multi_ch(const ScanParams& p, int ch, cudaStream_t stream) {
+  constexpr int NQ = kScanMultiF32;
+  const size_t smem = static_cast<size_t>(NQ) * p.query_floats * sizeof(float) +
+                      static_cast<size_t>(NQ) * kScanMultiWarps * p.k * sizeof(uint64_t);
+  switch (ch) {
+    case 1: return launch_scan_multi_kernel(scan_multi_topk_kernel<LPR, 1, SPARSE, NQ>, p, kNumSMs, kScanMultiThreads, smem, stream);
+    case 2: return launch_scan_multi_kernel(scan_multi_topk_kernel<LPR, 2, SPARSE, NQ>, p, kNumSMs, kScanMultiThreads, smem, stream);
+    case 4: return launch_scan_multi_kernel(scan_multi_topk_kernel<LPR, 4, SPARSE, NQ>, p, kNumSMs, kScanMultiThreads, smem, stream);
+    default: return launch_scan_multi_kernel(scan_multi_topk_kernel<LPR, 8, SPARSE, NQ>, p, kNumSMs, kScanMultiThreads, smem, stream);
+  }
+}
+
+// fp32 rows, kScanMultiF32 queries per pass
+template <bool SPARSE>
+int launch_scan_multi_variant(const ScanParams& p, int lpr, int ch, cudaStream_t stream) {
+  if (lpr == 32) return launch_scan_multi_ch<SPARSE, 32>(p, ch, stream);
+  if (lpr == 16) return launch_scan_multi_ch<SPARSE, 16>(p, ch, stream);
+  return launch_scan_multi_ch<SPARSE, 8>(p, ch, stream);
+}
+
+// bf16 rows on mma.sync, kScanMultiBf16 queries per pass
+template <bool SPARSE>
+int launch_scan_mma_multi_variant(const ScanParams& p, cudaStream_t stream) {
+  constexpr int NQ = kScanMultiBf16;
+  const int ks = (p.row_chunks + 3) / 4;
+  size_t smem = static_cast<size_t>(NQ) * p.query_floats * sizeof(float) +
+                static_cast<size_t>(NQ) * kScanMmaWarps * p.k * sizeof(uint64_t);
+  const int blocks = kNumSMs * kScanBlocksPerSM;
+  if (ks <= 4) return launch_scan_multi_kernel(scan_mma_topk_kernel<SPARSE, 1, 4, NQ>, p, blocks, kScanMmaThreads, smem, stream);
+  if (ks <= 8) return launch_scan_multi_kernel(scan_mma_topk_kernel<SPARSE, 1, 8, NQ>, p, blocks, kScanMmaThreads, smem, stream);
+  if (ks <= 12) return launch_scan_multi_kernel(scan_mma_topk_kernel<SPARSE, 1, 12, NQ>, p, blocks, kScanMmaThreads, smem, stream);
+  if (ks <= 16) return launch_scan_multi_kernel(scan_mma_topk_kernel<SPARSE, 1, 16, NQ>, p, blocks, kScanMmaThreads, smem, stream);
+  smem += static_cast<size_t>(3 * NQ) * ks * 16 * sizeof(uint32_t);
+  return launch_scan_multi_kernel(scan_mma_topk_kernel<SPARSE, 1, 0, NQ>, p, blocks, kScanMmaThreads, smem, stream);
 }
 
 }  // namespace pvdb

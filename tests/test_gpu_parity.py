@@ -714,3 +714,58 @@ def test_bf16_mma_scan_pages_large_k(store_factory):
     kth = exact[want[-1]]
     for r in set(rows[0].tolist()) ^ set(want.tolist()):
         assert abs(exact[r] - kth) <= 4e-6
+
+
+# ------------------------------------------------------------------ several queries per pass
+@pytest.mark.parametrize("kw", [{}, {"keep_f32": False, "bf16_mirror": True}], ids=["f32", "bf16"])
+@pytest.mark.parametrize("dim", [8, 20, 100, 384, 520, 1024, 1536])
+def test_exact_batches_share_a_pass_and_equal_single_queries(store_factory, monkeypatch, kw, dim):
+    """An exact batch (precision f32 / the bf16 rows of a bf16-only store) is scanned several queries per pass
+    (4 over fp32 rows, 2 over bf16 rows on mma.sync; scan_kernel.cuh).  Per query the arithmetic is the
+    single-query kernel's, so every query must come back with the SAME BITS it gets alone -- raw and
+    pre-normalised queries, zero queries, deleted rows, dense and sparse walks, ragged group sizes -- and k > 32
+    must quietly take the single-query kernels.  The oracle pins the values."""
+    n = 4099
+    prec = "f32" if not kw else "bf16"
+    s = store_factory(dim, **kw)
+    s.upsert_range(_gauss(n, dim, 500 + dim), 0)
+    dead = np.random.default_rng(5).choice(n, n // 5, replace=False)
+    s.delete_rows(dead)
+    active = np.ones(n, bool)
+    active[dead] = False
+    store = s.download()
+    pf = (np.arange(n) % 4) != 2
+    from picovdb_b200._native import kernel_launches as launches
+
+    for nq in (2, 3, 4, 5, 9):
+        queries = _gauss(nq, dim, 40 + nq)
+        queries[nq // 2] = 0.0
+        qn, _ = O.prepare_queries(queries, dim)
+        for k in (1, 10, 32, 33):
+            for prefilter in (None, pf):
+                l0 = launches()
+                b_s, b_r = s.search(queries, k, prefilter=prefilter, precision=prec, scan_only=True)
+                used = launches() - l0
+                width = 4 if prec == "f32" else 2
+                want = nq if k > 32 else (nq // width + (1 if nq % width >= 2 else 0) + (1 if nq % width == 1 else 0))
+                assert used == want, (nq, k, used, want)
+                n_s, n_r = s.search(qn, k, prefilter=prefilter, precision=prec, normalized=True, scan_only=True)
+                np.testing.assert_array_equal(n_r, b_r)   # (host-normalised queries differ in the last bit)
+                np.testing.assert_allclose(n_s, b_s, rtol=2e-6, atol=1e-6)
+                for qi in range(nq):
+                    o_s, o_r = s.search(queries[qi:qi + 1], k, prefilter=prefilter, precision=prec)
+                    np.testing.assert_array_equal(b_r[qi], o_r[0])
+                    np.testing.assert_array_equal(b_s[qi], o_s[0])
+                if prec == "f32":
+                    ref_s, ref_r = O.search(store, qn, k, active, prefilter)
+                    O.compare_topk(b_s, b_r, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+    # the switch: one launch per query again, same bits
+    queries = _gauss(6, dim, 77)
+    b_s, b_r = s.search(queries, 10, precision=prec, scan_only=True)
+    monkeypatch.setenv("PVDB_SCAN_NO_MULTI", "1")
+    l0 = launches()
+    o_s, o_r = s.search(queries, 10, precision=prec, scan_only=True)
+    assert launches() - l0 == 6
+    monkeypatch.delenv("PVDB_SCAN_NO_MULTI", raising=False)
+    np.testing.assert_array_equal(b_r, o_r)
+    np.testing.assert_array_equal(b_s, o_s)

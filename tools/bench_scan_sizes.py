@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Scan-kernel time vs shard size (fixed cost vs streaming part).  python tools/bench_scan_sizes.py"""
-import json, os, sys
+import json, os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -27,9 +27,11 @@ for rows in [int(x) for x in os.environ.get("PVDB_SIZES", "1024,16384,62500,1250
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     for j in range(n):
         st.search_dev(q[j % 64].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32", normalized=True, stream=stream)
+    host_us = (time.perf_counter() - t0) / n * 1e6
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / n * 1e3
-    print(json.dumps({"rows": rows, "us_per_scan": round(us, 2), "stream_us_at_7TBs": round(rows * dim * 4 / 7.0e6, 2)}), flush=True)
+    print(json.dumps({"rows": rows, "us_per_scan": round(us, 2), "host_enqueue_us": round(host_us, 2), "stream_us_at_7TBs": round(rows * dim * 4 / 7.0e6, 2)}), flush=True)
     st.close()
