@@ -151,16 +151,19 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
   // scratch; one exchange + merge launch then writes the final result.  The scan path exchanges
   // inside the scan kernel itself.  Every rank takes the same path (it depends on the arguments and
   // the store layout only), so all ranks consume the same exchange sequence numbers.
+  // ... unless several queries can share a pass (scan_kernel.cuh): then the local lists of the whole call go to
+  // scratch as well and ONE exchange + merge launch follows, instead of one exchanging scan per query.
+  const bool grouped = ex != nullptr && !batch && nq >= 2 && scan_multi_width(prec == PVDB_PREC_BF16, s->ldq, k) > 1;
   float* d_fin_scores = d_out_scores;
   int64_t* d_fin_rows = d_out_rows;
-  if (ex != nullptr && (batch || s->rows == 0)) {
+  if (ex != nullptr && (batch || grouped || s->rows == 0)) {
     PVDB_TRY(s->d_xloc.ensure(static_cast<size_t>(nq) * k * (sizeof(int64_t) + sizeof(float))));
     d_out_rows = static_cast<int64_t*>(s->d_xloc.ptr);
     d_out_scores = reinterpret_cast<float*>(d_out_rows + nq * k);
   }
   if (s->rows == 0) {  // only reached with an exchange: publish empty lists, collect the peers'
     PVDB_TRY(fill_empty(d_out_scores, d_out_rows, nq * k, st));
-    if (batch) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
+    if (batch || grouped) return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
     for (int64_t q = 0; q < nq; ++q)
       PVDB_TRY(launch_exchange_merge(ex, d_out_scores + q * k, d_out_rows + q * k, 1, k, d_fin_scores + q * k,
                                      d_fin_rows + q * k, st));
@@ -241,6 +244,10 @@ static int search_device(pvdb_store* s, const float* d_queries, int64_t nq, int 
     return PVDB_OK;
   }
   // scan path: TF32 requests with few queries are served by the exact fp32 scan
+  if (grouped) {
+    PVDB_TRY(search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st));
+    return launch_exchange_merge(ex, d_out_scores, d_out_rows, nq, k, d_fin_scores, d_fin_rows, st);
+  }
   return search_scan(s, prec == PVDB_PREC_BF16, d_qn, d_queries, nq, k, d_pref, d_out_scores, d_out_rows, st, ex);
 }
 

@@ -44,9 +44,15 @@ def test_self_mailbox_exchange_matches_plain_search(monkeypatch):
                 want_s, want_r = st.search(queries[:5], k, prefilter=prefilter, precision="f32")
                 for rep in range(3):                # consecutive launches alternate the slot parity
                     got_s, got_r = st.search_exchange(ex, queries[:5], k, prefilter=prefilter, precision="f32")
-                    launches += 5                   # scan path: one fused launch per query
+                    # scan path: k <= 32 scans several queries per pass into scratch and exchanges once;
+                    # beyond that one scan per query with the exchange fused into its last block
+                    launches += 1 if k <= 32 else 5
                     np.testing.assert_array_equal(got_r, want_r)
                     np.testing.assert_array_equal(got_s, want_s)
+                got_s, got_r = st.search_exchange(ex, queries[3:4], k, prefilter=prefilter, precision="f32")
+                launches += 1                       # a lone query: always the fused form
+                np.testing.assert_array_equal(got_r, want_r[3:4])
+                np.testing.assert_array_equal(got_s, want_s[3:4])
                 assert want_r.min() >= 1_000_000
         assert ex.launches() == launches
         for prec in ("tf32", "bf16"):               # batch path: one exchange + merge launch per call
