@@ -123,6 +123,11 @@ __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int mask) {
   return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
+// Device-scope fence for the "last block done" hand-over (lists -> fence -> ticket; ticket -> fence -> lists).
+// __threadfence() is the sequentially consistent fence (MEMBAR.SC.GPU): the acquire-release one is enough for a
+// fence-fence synchronisation through a relaxed atomic and is the cheaper instruction.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------- warp top-k list
 // A warp keeps its best candidates as a descending list of 32*S keys spread over the lanes:
 // entry e lives in slot e/32 of lane e%32.  Only the first k entries are ever read back; the tail
@@ -191,6 +196,49 @@ __device__ __forceinline__ void merge_list(WarpList<S>& L, uint64_t& thr, const 
       }
     }
   }
+}
+
+// Merge a descending list of k <= 32 keys in SHARED memory into a one-slot warp list with a bitonic network:
+// max(A[i], B[31 - i]) is a bitonic sequence holding the 32 best of the union; five compare-exchange stages sort
+// it.  Data independent (~5 x 2 shuffles), unlike the insertion loop of merge_list, whose cost grows with the
+// number of keys that qualify (~150 cycles each).
+__device__ __forceinline__ void bitonic_merge_shared(WarpList<1>& L, const uint64_t* src, int k, int lane) {
+  const int e = 31 - lane;
+  const uint64_t b = (e < k) ? src[e] : 0ull;
+  uint64_t v = L.slot[0] > b ? L.slot[0] : b;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = shfl_xor_u64(v, j);
+    const bool keep_max = (lane & j) == 0;
+    v = (keep_max == (v > o)) ? v : o;
+  }
+  L.slot[0] = v;
+}
+
+// Fold the lists the warps of a block left in shared memory (warp w at slist + w * k) into warp 0's list by a
+// binary tree: log2(n_warps) rounds, each a block barrier + one merge per surviving warp, instead of warp 0
+// merging the other n_warps - 1 lists one after the other.  Every warp of the block must call it.
+template <int S>
+__device__ __forceinline__ void block_tree_merge(WarpList<S>& L, uint64_t& thr, uint64_t* slist, int k, int warp, int lane,
+                                                 int n_warps) {
+  for (int step = 1; step < n_warps; step <<= 1) {
+    if ((warp & (2 * step - 1)) == 0 && warp + step < n_warps) {
+      if constexpr (S == 1) {
+        bitonic_merge_shared(L, slist + (warp + step) * k, k, lane);
+      } else {
+        merge_list<false, S>(L, thr, slist + (warp + step) * k, k, k, lane);
+      }
+      if (2 * step < n_warps) {   // read by the next round's survivor
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+          const int e = s * 32 + lane;
+          if (e < k) slist[warp * k + e] = L.slot[s];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if constexpr (S == 1) thr = L.get(k - 1);
 }
 
 template <int S>

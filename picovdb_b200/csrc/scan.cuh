@@ -37,6 +37,8 @@ struct ScanParams {
   uint64_t* partial;         // [gridDim.x][k] per-block lists
   unsigned int* ticket;      // last-block-done counter (self-resetting)
   uint64_t* next_upper;      // receives the k-th key of this pass (0 when fewer than k found)
+  unsigned long long* floor_key;  // max over the blocks of "k-th key of the block's list": no key below it can be
+                             // in the top k, so the last block admits nothing smaller (self-resetting)
   float* out_scores;         // [k]
   int64_t* out_rows;         // [k]
   int64_t row_base;

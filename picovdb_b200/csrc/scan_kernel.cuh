@@ -74,6 +74,21 @@ __device__ __forceinline__ void sparse_walk(const ScanParams& p, int64_t first_w
   if (cnt > 0u) step(ring, head, cnt);   // the one partial step of this warp
 }
 
+// -DPVDB_SCAN_TRACE (variant builds only, tools/scan_trace.py): %globaltimer stamps of the phases of one launch,
+// written behind the ticket word (block 0: slots 0-3, the last block: slots 4-6).
+#ifdef PVDB_SCAN_TRACE
+__device__ __forceinline__ void scan_trace(const ScanParams& p, int slot, bool who) {
+  if (who && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    reinterpret_cast<unsigned long long*>(p.ticket)[8 + slot] = t;
+  }
+}
+#define PVDB_TRACE(slot, who) scan_trace(p, slot, who)
+#else
+#define PVDB_TRACE(slot, who) ((void)0)
+#endif
+
 // What every scan variant does first: programmatic-dependent-launch bookkeeping, then the normalised query
 // goes to shared memory (sq[0 .. query_floats), zero padded).
 __device__ __forceinline__ void scan_prologue(const ScanParams& p, float* sq) {
@@ -122,49 +137,65 @@ __device__ __forceinline__ void scan_prologue(const ScanParams& p, float* sq) {
 
 // What every scan variant does last: block merge of the warp lists, last-block-done merge of the per-block
 // lists, optional cross-GPU exchange, result write-out.
-template <int S>
+// The merges used to be the scan's fixed cost (tools/scan_trace.py on a 1024-row store: block merge 3.6 us,
+// folding the 296 block lists 5.8 us, final merge 4.9 us of 17 us per launch): every qualifying key cost an
+// insertion (~150 cycles of dependent shuffles) and one warp did each block-level merge alone.  Now
+//  * block-level merges are binary trees over the warps (block_tree_merge; bitonic networks for k <= 32);
+//  * every block raises `floor_key` to the k-th key of its list before it takes its ticket.  The block with
+//    the largest such key holds k keys at or above it, so nothing below the final floor can be in the top k:
+//    the last block starts from that threshold and the 296 lists contribute a few dozen keys, not 296 k.
+// HB: heads of per-block lists a warp of the last block fetches at once (one L2 round trip when
+// n_warps * HB covers the grid).
+template <int S, int HB>
 __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L, uint64_t& thr, uint64_t* slist) {
   __shared__ unsigned s_is_last;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int k = p.k;
   const int n_warps = static_cast<int>(blockDim.x >> 5);   // (the mma variant runs smaller blocks)
-  // ---- block merge: warp 0 folds the other warps' lists into its own
+  // ---- block merge
   store_list(L, slist + warp * k, k, lane);
   __syncthreads();
   // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  block_tree_merge<S>(L, thr, slist, k, warp, lane, n_warps);
   if (warp == 0) {
-    for (int w2 = 1; w2 < n_warps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
     store_list(L, p.partial + static_cast<size_t>(blockIdx.x) * k, k, lane);
-    __threadfence();
+    const uint64_t kth = L.get(k - 1);
+    fence_acq_rel_gpu();
     __syncwarp();
     if (lane == 0) {
+      if (kth != 0ull) atomicMax(p.floor_key, static_cast<unsigned long long>(kth));
       const unsigned t = atomicAdd(p.ticket, 1u);
       s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
   }
   __syncthreads();
+  PVDB_TRACE(3, blockIdx.x == 0);
   if (s_is_last == 0u) return;
 
   // ---- last block: merge all per-block lists and emit the result
-  __threadfence();
+  PVDB_TRACE(4, true);
+  fence_acq_rel_gpu();
   L.clear();
+  // keys >= floor qualify (the admission test below is "key > thr"); the load travels with the first heads
+  const uint64_t floor_key = __ldcg(p.floor_key);
   thr = 0ull;
-  // Each warp takes every 16th block list.  The heads (first 32 keys) of eight lists are fetched
+  // Each warp takes every n_warps-th block list.  The heads (first 32 keys) of HB lists are fetched
   // together so the L2 round trips overlap; a list whose whole head qualified continues through
   // the general path.
-  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += n_warps * 8) {
-    uint64_t head[8];
+  for (int b0 = warp; b0 < static_cast<int>(gridDim.x); b0 += n_warps * HB) {
+    uint64_t head[HB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < HB; ++j) {
       const int b = b0 + j * n_warps;
       head[j] = (b < static_cast<int>(gridDim.x) && lane < k)
                     ? load_key<true>(p.partial + static_cast<size_t>(b) * k + lane)
                     : 0ull;
     }
+    if (b0 == warp) thr = floor_key ? floor_key - 1ull : 0ull;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < HB; ++j) {
       const int b = b0 + j * n_warps;
       if (b >= static_cast<int>(gridDim.x)) break;
       unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
@@ -175,17 +206,19 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
         const uint64_t x = shfl_u64(head[j], srcl);
         if (x > thr) {
           L.insert(x, lane);
-          thr = L.get(k - 1);
+          const uint64_t kth = L.get(k - 1);
+          if (kth > thr) thr = kth;   // (never below the floor)
         }
       }
       if (head_all && k > 32) merge_list<true, S>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
     }
   }
   __syncthreads();  // everyone is done reading slist from the first merge
+  PVDB_TRACE(5, true);
   store_list(L, slist + warp * k, k, lane);
   __syncthreads();
+  block_tree_merge<S>(L, thr, slist, k, warp, lane, n_warps);
   if (warp == 0) {
-    for (int w2 = 1; w2 < n_warps; ++w2) merge_list<false, S>(L, thr, slist + w2 * k, k, k, lane);
     int64_t out_base = p.row_base;
     if (p.xv.world > 0) {
       // ---- cross-GPU exchange, fused (exchange.cuh): this GPU's list goes into every peer's
@@ -221,9 +254,11 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
       }
     }
     const uint64_t kth = L.get(k - 1);
+    PVDB_TRACE(6, true);
     if (lane == 0) {
       *p.next_upper = kth;
       *p.ticket = 0u;
+      *p.floor_key = 0ull;
     }
   }
 }
@@ -283,9 +318,11 @@ __device__ __forceinline__ void scan_prologue_multi(const ScanParams& p, float* 
   __syncthreads();
 }
 
-// Finish: per-query block merge (warp q folds every warp's list of query q), one ticket per block, and in the
-// last block the warps split the per-block lists by query (warp w: query w % NQ, every (n_warps / NQ)-th
-// block list) before one warp per query folds those and writes the result rows of its query.
+// Finish, as scan_finish but for NQ lists per warp (k <= 32: bitonic merges throughout): the block-level tree
+// carries all NQ lists of a warp per round, every block raises the per-query floor (floor_key[q]) before its
+// ticket, and in the last block the warps split the per-block lists by query (warp w: query w % NQ, every
+// (n_warps / NQ)-th block list, starting from the query's floor) before one warp per query folds those partial
+// results and writes the result rows of its query.
 template <int NQ>
 __device__ __forceinline__ void scan_finish_multi(const ScanParams& p, WarpList<1> (&L)[NQ], uint64_t* slist) {
   __shared__ unsigned s_is_last;
@@ -295,40 +332,59 @@ __device__ __forceinline__ void scan_finish_multi(const ScanParams& p, WarpList<
   const int n_warps = static_cast<int>(blockDim.x >> 5);   // a multiple of NQ
   const int grid = static_cast<int>(gridDim.x);
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) store_list(L[q], slist + (q * n_warps + warp) * k, k, lane);
+  for (int q = 0; q < NQ; ++q) store_list(L[q], slist + (warp * NQ + q) * k, k, lane);
   __syncthreads();
   // the previous scan's last block may still be merging the per-block lists (and owns the ticket)
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  WarpList<1> M;
-  uint64_t thr = 0ull;
-  M.clear();
-  if (warp < NQ) {
-    for (int w2 = 0; w2 < n_warps; ++w2) merge_list<false, 1>(M, thr, slist + (warp * n_warps + w2) * k, k, k, lane);
-    store_list(M, p.partial + (static_cast<size_t>(blockIdx.x) * NQ + warp) * k, k, lane);
-    __threadfence();
+  for (int step = 1; step < n_warps; step <<= 1) {
+    if ((warp & (2 * step - 1)) == 0 && warp + step < n_warps) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) bitonic_merge_shared(L[q], slist + ((warp + step) * NQ + q) * k, k, lane);
+      if (2 * step < n_warps) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) store_list(L[q], slist + (warp * NQ + q) * k, k, lane);
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(p.ticket, 1u);
-    s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+  if (warp == 0) {
+    uint64_t kth[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      store_list(L[q], p.partial + (static_cast<size_t>(blockIdx.x) * NQ + q) * k, k, lane);
+      kth[q] = L[q].get(k - 1);
+    }
+    fence_acq_rel_gpu();
+    __syncwarp();
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q)
+        if (kth[q] != 0ull) atomicMax(p.floor_key + q, static_cast<unsigned long long>(kth[q]));
+      const unsigned t = atomicAdd(p.ticket, 1u);
+      s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
+    }
   }
   __syncthreads();
   if (s_is_last == 0u) return;
 
   // ---- last block
-  __threadfence();
+  fence_acq_rel_gpu();
+  constexpr int HB = 40;   // 4 warps per query x 40 heads: one L2 round trip for 148 lists, two for 296
   const int q = warp % NQ, part = warp / NQ, parts = n_warps / NQ;
+  WarpList<1> M;
   M.clear();
-  thr = 0ull;
-  for (int b0 = part; b0 < grid; b0 += parts * 8) {
-    uint64_t head[8];
+  const uint64_t floor_key = __ldcg(p.floor_key + q);
+  uint64_t thr = 0ull;
+  for (int b0 = part; b0 < grid; b0 += parts * HB) {
+    uint64_t head[HB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < HB; ++j) {
       const int b = b0 + j * parts;
       head[j] = (b < grid && lane < k) ? load_key<true>(p.partial + (static_cast<size_t>(b) * NQ + q) * k + lane) : 0ull;
     }
+    if (b0 == part) thr = floor_key ? floor_key - 1ull : 0ull;   // keys >= floor qualify
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < HB; ++j) {
       unsigned m = __ballot_sync(0xffffffffu, head[j] > thr);
       while (m) {
         const int srcl = __ffs(m) - 1;
@@ -336,17 +392,17 @@ __device__ __forceinline__ void scan_finish_multi(const ScanParams& p, WarpList<
         const uint64_t x = shfl_u64(head[j], srcl);
         if (x > thr) {
           M.insert(x, lane);
-          thr = M.get(k - 1);
+          const uint64_t kth = M.get(k - 1);
+          if (kth > thr) thr = kth;   // (never below the floor)
         }
       }
     }
   }
-  store_list(M, slist + (q * parts + part) * k, k, lane);   // (every warp passed the block merge's reads: two barriers ago)
+  store_list(M, slist + (q * parts + part) * k, k, lane);   // (the tree's last barrier is behind every warp)
   __syncthreads();
-  if (warp < NQ) {
-    M.clear();
-    thr = 0ull;
-    for (int p2 = 0; p2 < parts; ++p2) merge_list<false, 1>(M, thr, slist + (warp * parts + p2) * k, k, k, lane);
+  if (warp < NQ) {   // warp w finishes query w
+    M.slot[0] = (lane < k) ? slist[(warp * parts) * k + lane] : 0ull;
+    for (int p2 = 1; p2 < parts; ++p2) bitonic_merge_shared(M, slist + (warp * parts + p2) * k, k, lane);
     if (warp < p.nq && lane < k) {
       const uint64_t key = M.slot[0];
       const int64_t o = p.qsel[warp] * k + lane;
@@ -354,7 +410,11 @@ __device__ __forceinline__ void scan_finish_multi(const ScanParams& p, WarpList<
       p.out_rows[o] = key ? p.row_base + static_cast<int64_t>(key_row(key)) : -1ll;
     }
   }
-  if (threadIdx.x == 0) *p.ticket = 0u;
+  if (threadIdx.x == 0) {
+    *p.ticket = 0u;
+#pragma unroll
+    for (int q2 = 0; q2 < NQ; ++q2) p.floor_key[q2] = 0ull;
+  }
 }
 
 constexpr int kScanMultiThreads = 512;  // x 1 block per SM: 128 registers per thread (NQ accumulators, lists, thresholds)
@@ -515,7 +575,9 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
   const int gi = lane / LPR;
   const int k = p.k;
 
+  PVDB_TRACE(0, blockIdx.x == 0);
   scan_prologue(p, sq);
+  PVDB_TRACE(1, blockIdx.x == 0);
   const float4* sq4 = reinterpret_cast<const float4*>(sq);
 
   const uint64_t upper = p.upper ? *p.upper : ~0ull;
@@ -625,7 +687,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanBlocksPerSM) scan_topk_kern
                      });
   }
 
-  scan_finish<S>(p, L, thr, slist);
+  PVDB_TRACE(2, blockIdx.x == 0);
+  scan_finish<S, (S == 1 ? 10 : 8)>(p, L, thr, slist);
 }
 
 
@@ -874,7 +937,7 @@ __global__ void __launch_bounds__(kScanMmaThreads, kScanBlocksPerSM) scan_mma_to
                        score_rows(row, on);
                      });
   }
-  if constexpr (NQ == 1) scan_finish<S>(p, L[0], thr[0], slist);
+  if constexpr (NQ == 1) scan_finish<S, (S == 1 ? 20 : 8)>(p, L[0], thr[0], slist);
   else scan_finish_multi<NQ>(p, L, slist);
 }
 
