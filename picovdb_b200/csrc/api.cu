@@ -42,7 +42,7 @@ static int search_scan(pvdb_store* s, bool bf16, const float* d_qn, const float*
                        pvdb_exchange* ex = nullptr, const int* h_sel = nullptr) {
   const int grid = scan_grid_blocks();
   const size_t list_bytes = static_cast<size_t>(grid) * kFusedK * sizeof(uint64_t);
-  PVDB_TRY(s->d_partial.ensure(list_bytes + 128));   // ticket, paging bound (+ the phase stamps of trace builds)
+  PVDB_TRY(s->d_partial.ensure(list_bytes + 256));   // ticket, paging bound (+ the phase stamps of trace builds)
   unsigned char* ctrl = static_cast<unsigned char*>(s->d_partial.ptr) + list_bytes;
   if (s->partial_gen_inited != s->d_partial.gen) {
     PVDB_CUDA(cudaMemsetAsync(ctrl, 0, 64, st));
@@ -406,11 +406,11 @@ extern "C" int pvdb_search_where(pvdb_store_t* s, const float* queries, int64_t 
 
 #ifdef PVDB_SCAN_TRACE
 // variant builds only (tools/scan_trace.py): the phase stamps of the store's last scan launch
-extern "C" int pvdb_debug_scan_trace(pvdb_store_t* s, unsigned long long* out8) {
+extern "C" int pvdb_debug_scan_trace(pvdb_store_t* s, unsigned long long* out24) {
   PVDB_ENTER(s);
   const size_t list_bytes = static_cast<size_t>(scan_grid_blocks()) * kFusedK * sizeof(uint64_t);
   PVDB_CUDA(cudaDeviceSynchronize());
-  PVDB_CUDA(cudaMemcpy(out8, static_cast<unsigned char*>(s->d_partial.ptr) + list_bytes + 64, 64, cudaMemcpyDeviceToHost));
+  PVDB_CUDA(cudaMemcpy(out24, static_cast<unsigned char*>(s->d_partial.ptr) + list_bytes + 64, 192, cudaMemcpyDeviceToHost));
   return PVDB_OK;
 }
 #endif

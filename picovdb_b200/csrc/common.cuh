@@ -215,6 +215,19 @@ __device__ __forceinline__ void bitonic_merge_shared(WarpList<1>& L, const uint6
   L.slot[0] = v;
 }
 
+// The same network for two one-slot lists held in registers (both descending over the lanes).
+__device__ __forceinline__ uint64_t bitonic_merge_regs(uint64_t a, uint64_t b, int lane) {
+  const uint64_t br = shfl_u64(b, 31 - lane);
+  uint64_t v = a > br ? a : br;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = shfl_xor_u64(v, j);
+    const bool keep_max = (lane & j) == 0;
+    v = (keep_max == (v > o)) ? v : o;
+  }
+  return v;
+}
+
 // Fold the lists the warps of a block left in shared memory (warp w at slist + w * k) into warp 0's list by a
 // binary tree: log2(n_warps) rounds, each a block barrier + one merge per surviving warp, instead of warp 0
 // merging the other n_warps - 1 lists one after the other.  Every warp of the block must call it.

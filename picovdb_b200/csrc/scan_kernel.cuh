@@ -165,7 +165,7 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
     fence_acq_rel_gpu();
     __syncwarp();
     if (lane == 0) {
-      if (kth != 0ull) atomicMax(p.floor_key, static_cast<unsigned long long>(kth));
+      if (S != 1 && kth != 0ull) atomicMax(p.floor_key, static_cast<unsigned long long>(kth));   // (k <= 32 folds with bitonic trees: no threshold)
       const unsigned t = atomicAdd(p.ticket, 1u);
       s_is_last = (t == gridDim.x - 1) ? 1u : 0u;
     }
@@ -177,9 +177,10 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
   // ---- last block: merge all per-block lists and emit the result
   PVDB_TRACE(4, true);
   fence_acq_rel_gpu();
+  PVDB_TRACE(7, true);
   L.clear();
   // keys >= floor qualify (the admission test below is "key > thr"); the load travels with the first heads
-  const uint64_t floor_key = __ldcg(p.floor_key);
+  const uint64_t floor_key = S != 1 ? __ldcg(p.floor_key) : 0ull;
   thr = 0ull;
   // Each warp takes every n_warps-th block list.  The heads (first 32 keys) of HB lists are fetched
   // together so the L2 round trips overlap; a list whose whole head qualified continues through
@@ -194,6 +195,20 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
                     : 0ull;
     }
     if (b0 == warp) thr = floor_key ? floor_key - 1ull : 0ull;
+    PVDB_TRACE(8, b0 == warp && head[0] != 1ull);
+    if constexpr (S == 1) {
+      // k <= 32: a list is one register per lane.  Pairwise bitonic merges of the HB heads (a tree: the merges
+      // of a level are independent, so their shuffles overlap), then one merge into the running list --
+      // ~0.5 us per HB lists whatever the data; insertions cost ~0.1 us per qualifying key (traced: 4-5 us for
+      // this loop even with the floor, ~200 keys of 2960 qualify on Gaussian rows).
+#pragma unroll
+      for (int w = 1; w < HB; w <<= 1) {
+#pragma unroll
+        for (int j = 0; j + w < HB; j += 2 * w) head[j] = bitonic_merge_regs(head[j], head[j + w], lane);
+      }
+      L.slot[0] = bitonic_merge_regs(L.slot[0], head[0], lane);
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < HB; ++j) {
       const int b = b0 + j * n_warps;
@@ -213,6 +228,7 @@ __device__ __forceinline__ void scan_finish(const ScanParams& p, WarpList<S>& L,
       if (head_all && k > 32) merge_list<true, S>(L, thr, p.partial + static_cast<size_t>(b) * k + 32, k - 32, k, lane);
     }
   }
+  PVDB_TRACE(9, true);
   __syncthreads();  // everyone is done reading slist from the first merge
   PVDB_TRACE(5, true);
   store_list(L, slist + warp * k, k, lane);

@@ -43,16 +43,17 @@ for rows in (1024, 125_000, 1_000_000):
         st.search_dev(q[j % 64].data_ptr(), 1, k, out_s.data_ptr(), out_r.data_ptr(), precision="f32", normalized=True, stream=stream)
         e1.record()
         torch.cuda.synchronize()
-        t = np.zeros(8, dtype=np.uint64)
+        t = np.zeros(24, dtype=np.uint64)
         N.check(lib.pvdb_debug_scan_trace(st.handle, t.ctypes.data_as(C.c_void_p)))
         t = t.astype(np.int64)
         if j >= 10:
             rec.append([t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[0], t[5] - t[4], t[6] - t[5], t[6] - t[0],
-                        e0.elapsed_time(e1) * 1e6])
+                        e0.elapsed_time(e1) * 1e6, t[7] - t[4], t[8] - t[7], t[9] - t[8], t[5] - t[9]])
     med = np.median(np.array(rec, dtype=np.float64), axis=0) / 1e3
     print(json.dumps({"rows": rows, "dim": dim, "k": k, "us": {
         "block0_prologue": round(med[0], 2), "block0_walk": round(med[1], 2), "block0_merge_ticket": round(med[2], 2),
         "kernel_entry_to_last_block_start": round(med[3], 2), "last_block_fold_block_lists": round(med[4], 2),
+        "last_block_fold_parts(fence,first_heads_arrive,inserts+second_round,barrier)": [round(med[8], 2), round(med[9], 2), round(med[10], 2), round(med[11], 2)],
         "last_block_final_merge": round(med[5], 2), "block0_entry_to_result": round(med[6], 2),
         "cuda_events_around_the_call": round(med[7], 2)}}), flush=True)
     st.close()
