@@ -29,6 +29,8 @@ CASES = [  # rows, dim, queries, k, bf16-only
     (3_000_000, 128, 64, 10, True),
     (1_000_000, 1024, 64, 10, True),
 ]
+if os.environ.get("PVDB_CASES"):   # e.g. PVDB_CASES=1,3 (for ncu captures)
+    CASES = [CASES[int(i)] for i in os.environ["PVDB_CASES"].split(",")]
 for rows, dim, nq, k, b16 in CASES:
     st = DeviceStore(dim, device=0, reserve_rows=rows, **({"keep_f32": False, "bf16_mirror": True} if b16 else {}))
     gen = torch.Generator(device=dev).manual_seed(123)
