@@ -506,26 +506,72 @@ __global__ void __launch_bounds__(kScanMultiThreads, 1) scan_multi_topk_kernel(c
         }
       }
     }
+    // Reduce the V = NQ * R partial sums over the LPR lanes of the group as a reduce-SCATTER: each butterfly
+    // stage halves the values a lane still carries (the lane with the stage's bit set keeps the upper half), so
+    // the stages cost V/2 + V/4 + ... shuffles instead of V each (16 instead of 80 at dim 384), and the
+    // candidate tests below run once per query, not once per (query, row).  Every total is formed by the same
+    // additions as the plain butterfly of the single-query kernel (own + partner at xor LPR/2, LPR/4, ...).
+    constexpr int V = NQ * R;
+    float vals[V];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
+      for (int r = 0; r < R; ++r) vals[q * R + r] = acc[q][r];
+    }
+    constexpr int LL = LPR == 32 ? 5 : (LPR == 16 ? 4 : 3);
+    constexpr int LV = V == 64 ? 6 : (V == 32 ? 5 : (V == 16 ? 4 : (V == 8 ? 3 : (V == 4 ? 2 : (V == 2 ? 1 : 0)))));
+    static_assert((1 << LV) == V, "NQ * R must be a power of two");
+    constexpr int NS = LL < LV ? LL : LV;          // halving stages
+    constexpr int HELD = 1 << (LV - NS);           // totals a lane ends up with
 #pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) acc[q][r] += __shfl_xor_sync(0xffffffffu, acc[q][r], o);
+    for (int st = 0; st < LL; ++st) {
+      const int m = LPR >> (st + 1);
+      if (st < NS) {
+        const int h = V >> (st + 1);
+        const bool upper = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = upper ? vals[i] : vals[i + h];
+          const float keep = upper ? vals[i + h] : vals[i];
+          vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+      } else {
+        vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], m);
       }
     }
+    // total j of this lane is value (top << (LV - NS)) | j, top = the NS high bits of the lane's index in its
+    // group; values are numbered q * R + r; when V < LPR a total is replicated on LPR / V lanes (the first counts)
+    const int top = sub >> (LL - NS);
+    const bool primary = (sub & ((1 << (LL - NS)) - 1)) == 0;
+    uint64_t key[HELD];
+    int kq[HELD];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int j = 0; j < HELD; ++j) {
+      const int v = (top << (LV - NS)) | j;
+      const int r = v & (R - 1);
+      kq[j] = v / R;
+      bool onv = false;
+      int64_t rowv = 0;
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        if (q >= nq) break;   // (warp-uniform) the last launch of a call may carry fewer than NQ queries
-        const float sc = acc[q][r];
-        const uint64_t key = (on[r] && sc == sc) ? make_key(sc, static_cast<uint32_t>(row[r])) : 0ull;
-        unsigned m = __ballot_sync(0xffffffffu, sub == 0 && key > thr[q]);
+      for (int rr = 0; rr < R; ++rr) {
+        if (r == rr) {
+          onv = on[rr];
+          rowv = row[rr];
+        }
+      }
+      const float sc = vals[j];
+      key[j] = (primary && onv && sc == sc) ? make_key(sc, static_cast<uint32_t>(rowv)) : 0ull;
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (q >= nq) break;   // (warp-uniform) the last launch of a call may carry fewer than NQ queries
+#pragma unroll
+      for (int j = 0; j < HELD; ++j) {
+        unsigned m = __ballot_sync(0xffffffffu, kq[j] == q && key[j] > thr[q]);
         while (m) {
           const int srcl = __ffs(m) - 1;
           m &= m - 1;
-          const uint64_t x = shfl_u64(key, srcl);
+          const uint64_t x = shfl_u64(key[j], srcl);
           if (x > thr[q]) {
             L[q].insert(x, lane);
             thr[q] = L[q].get(k - 1);

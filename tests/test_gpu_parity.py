@@ -769,3 +769,53 @@ def test_exact_batches_share_a_pass_and_equal_single_queries(store_factory, monk
     monkeypatch.delenv("PVDB_SCAN_NO_MULTI", raising=False)
     np.testing.assert_array_equal(b_r, o_r)
     np.testing.assert_array_equal(b_s, o_s)
+
+
+def test_exact_batches_edge_cases(store_factory):
+    """Several queries per pass at the edges: rows too wide for four queries to share shared memory (the call
+    quietly takes one pass per query), a store whose rows are all deleted (padding only), fewer live rows than k,
+    a store smaller than one warp step, and 33 queries (8 groups of 4 + a lone remainder) against the oracle."""
+    from picovdb_b200._native import kernel_launches as launches
+
+    # dim 12000: 4 x 48 KB of queries do not fit next to the lists -> single-query kernels, same answers
+    dim, n = 12000, 300
+    s = store_factory(dim)
+    s.upsert_range(_gauss(n, dim, 1), 0)
+    store = s.download()
+    q = _gauss(3, dim, 2)
+    qn, _ = O.prepare_queries(q, dim)
+    l0 = launches()
+    sc, rows = s.search(q, 5, precision="f32")
+    assert launches() - l0 == 3
+    ref_s, ref_r = O.search(store, qn, 5)
+    O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+
+    for kw, prec in (({}, "f32"), ({"keep_f32": False, "bf16_mirror": True}, "bf16")):
+        dim, n, k = 72, 700, 10
+        s = store_factory(dim, **kw)
+        s.upsert_range(_gauss(n, dim, 3), 0)
+        q = _gauss(33, dim, 4)
+        single = [s.search(q[i:i + 1], k, precision=prec) for i in range(33)]
+        sc, rows = s.search(q, k, precision=prec, scan_only=True)
+        np.testing.assert_array_equal(rows, np.concatenate([r for _, r in single]))
+        np.testing.assert_array_equal(sc, np.concatenate([x for x, _ in single]))
+        if prec == "f32":
+            qn, _ = O.prepare_queries(q, dim)
+            ref_s, ref_r = O.search(s.download(), qn, k)
+            O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
+        # fewer live rows than k, then none at all
+        s.delete_rows(np.arange(4, n))
+        sc, rows = s.search(q[:5], k, precision=prec, scan_only=True)
+        assert (rows[:, :4] >= 0).all() and (rows[:, :4] < 4).all() and (rows[:, 4:] == -1).all()
+        assert np.isneginf(sc[:, 4:]).all() and np.all(np.diff(sc[:, :4], axis=1) <= 0)
+        s.delete_rows(np.arange(0, 4))
+        sc, rows = s.search(q[:5], k, precision=prec, scan_only=True)
+        assert (rows == -1).all() and np.isneginf(sc).all()
+        # a store smaller than one warp step
+        t = store_factory(dim, **kw)
+        t.upsert_range(_gauss(3, dim, 5), 0)
+        sc, rows = t.search(q[:4], 2, precision=prec, scan_only=True)
+        for i in range(4):
+            o_s, o_r = t.search(q[i:i + 1], 2, precision=prec)
+            np.testing.assert_array_equal(rows[i], o_r[0])
+            np.testing.assert_array_equal(sc[i], o_s[0])
