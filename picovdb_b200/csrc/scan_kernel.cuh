@@ -1,5 +1,5 @@
-// The scan kernel template and its per-variant launcher.  Included by scan_inst_*.cu (one
-// translation unit per (dtype, sparse) pair so the 96 instantiations compile in parallel).
+// The scan kernel templates and their per-variant launchers.  Included by scan_inst_*.cu (one translation
+// unit per (kernel family, dtype, sparse) so the ~150 instantiations compile in parallel).
 #pragma once
 
 #include <cstdlib>
