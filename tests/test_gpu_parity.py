@@ -790,6 +790,19 @@ def test_exact_batches_edge_cases(store_factory):
     ref_s, ref_r = O.search(store, qn, 5)
     O.compare_topk(sc, rows, ref_s, ref_r, rtol=F32_RTOL, atol=F32_ATOL)
 
+    # the widest rows that still share passes (147 KB / 90 KB of dynamic shared memory per block)
+    for dim, kw, prec, width in ((8192, {}, "f32", 4), (4096, {"keep_f32": False, "bf16_mirror": True}, "bf16", 2)):
+        s = store_factory(dim, **kw)
+        s.upsert_range(_gauss(200, dim, 6), 0)
+        q = _gauss(width + 1, dim, 7)
+        l0 = launches()
+        sc, rows = s.search(q, 10, precision=prec, scan_only=True)
+        assert launches() - l0 == 2                      # one shared pass + the lone remainder
+        for i in range(width + 1):
+            o_s, o_r = s.search(q[i:i + 1], 10, precision=prec)
+            np.testing.assert_array_equal(rows[i], o_r[0])
+            np.testing.assert_array_equal(sc[i], o_s[0])
+
     for kw, prec in (({}, "f32"), ({"keep_f32": False, "bf16_mirror": True}, "bf16")):
         dim, n, k = 72, 700, 10
         s = store_factory(dim, **kw)
