@@ -71,6 +71,27 @@ class RowSeq:
             return self._over[row]
         return self._make(chunk[0] + off)
 
+    def getter(self) -> Callable[[int], Any]:
+        """``get(row)`` for rows already known to be in [0, len): what result assembly calls Q * k times per
+        query (pico_vdb.py:753-775).  A store of explicit rows only is ONE list, so this is ``list.__getitem__``;
+        otherwise a closure without the negative-index / slice handling of ``__getitem__``.  Valid until the
+        sequence is next extended or replaced (queries hold the read lock)."""
+        if len(self._chunks) == 1 and isinstance(self._chunks[0], list):
+            return self._chunks[0].__getitem__
+        starts, chunks, over, make = self._starts, self._chunks, self._over, self._make
+        locate = bisect.bisect_right
+
+        def get(row: int) -> Any:
+            c = locate(starts, row) - 1
+            chunk = chunks[c]
+            if type(chunk) is list:
+                return chunk[row - starts[c]]
+            if over and row in over:
+                return over[row]
+            return make(chunk[0] + row - starts[c])
+
+        return get
+
     def __setitem__(self, row: int, value: Any) -> None:
         row = self._norm(int(row))
         c, off = self._locate(row)

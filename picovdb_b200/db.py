@@ -1055,23 +1055,25 @@ class PicoVectorDB:
             self._last_topk_strategy = (
                 "argsort" if (k_eff / n_cand) > self._argsort_threshold else "argpartition"
             )
-            docs = self._docs
+            get_doc = self._docs.getter()
             n_slots = len(self._ids)
             recheck = callable(where)
             out: list[list[dict[str, Any]]] = []
-            for qi in range(num_q):
+            # one bulk conversion to Python numbers for the whole batch (tolist() of a float32 array yields
+            # Python floats: the `float(score)` of the reference's records, pico_vdb.py:770)
+            for q_rows, q_scores in zip(rows.tolist(), scores.tolist()):
                 hits: list[dict[str, Any]] = []
-                for row, score in zip(rows[qi].tolist(), scores[qi].tolist()):
+                for row, score in zip(q_rows, q_scores):
                     if row < 0 or row >= n_slots:
                         continue
-                    doc = docs[row]
+                    doc = get_doc(row)
                     if doc is None:
                         continue
                     if better_than is not None and score < better_than:
                         continue
                     if recheck and not where(doc):  # type: ignore[operator]
                         continue
-                    hits.append({**doc, K_METRICS: float(score)})
+                    hits.append({**doc, K_METRICS: score})
                     if len(hits) == top_k:
                         break
                 out.append(hits)

@@ -58,6 +58,23 @@ def test_rowseq_behaves_like_a_list():
     assert again == seq and again.implicit_rows == 8
 
 
+def test_rowseq_getter_matches_getitem():
+    """``getter()`` is what query() calls per returned row: the list's own __getitem__ for a store of
+    explicit rows, a closure over the chunk table otherwise -- same values as ``seq[row]`` everywhere."""
+    plain = RowSeq(lambda i: {"_id_": i}, [{"a": i} for i in range(50)])
+    assert plain.getter().__self__ is plain._chunks[0]          # no wrapper at all
+    mixed = RowSeq(lambda i: {"_id_": i}, [{"a": i} for i in range(5)])
+    mixed.extend_range(100, 1000)
+    mixed.extend([{"b": i} for i in range(7)])
+    mixed.extend_range(5000, 3)
+    mixed[17] = {"over": 1}
+    mixed[2] = None
+    get = mixed.getter()
+    for row in range(len(mixed)):
+        assert get(row) == mixed[row]
+    assert get(17) == {"over": 1} and get(2) is None and get(5 + 999) == {"_id_": 1099} and get(1012) == {"_id_": 5000}
+
+
 def test_idmap_behaves_like_a_dict():
     m = IdMap()
     m["a"] = 0
