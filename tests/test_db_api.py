@@ -99,6 +99,37 @@ def test_upsert_validation_messages(make_db):
         db.query(np.zeros((1, 2, 4), np.float32))
 
 
+def test_upsert_in_blocks_matches_one_block(make_db, monkeypatch):
+    """upsert() sends its vectors to the device in blocks through one reused staging array.  With the block
+    shrunk to 256 rows a 1000-item call spans four blocks: ids repeated across blocks keep their LAST vector,
+    updates of rows appended earlier in the same call work, a validation error half way commits what came
+    before it (pico_vdb.py:428-449), and the result equals the oracle DB's."""
+    from oracle import picovdb_oracle as O
+
+    monkeypatch.setattr(dbmod, "_UPSERT_BLOCK_BYTES", 1)
+    dim, n = 8, 1000
+    rng = np.random.default_rng(5)
+    vecs = rng.standard_normal((n + 300, dim)).astype(np.float32)
+    items = [{K_VECTOR: vecs[i], K_ID: f"id{i % 900}", "n": i} for i in range(n)]      # ids 0..99 appear twice
+    db = make_db(dim=dim)
+    odb = O.OracleDB(dim)
+    rep, orep = db.upsert(items), odb.upsert(items)
+    assert rep == orep and len(db) == 900
+    for probe in (vecs[950], vecs[50], vecs[500]):
+        got, want = db.query(probe, top_k=3), odb.query(probe, top_k=3)
+        assert ids_of(got) == ids_of(want)
+        np.testing.assert_allclose([g[K_METRICS] for g in got], [w[K_METRICS] for w in want], rtol=1e-5, atol=2e-6)
+    assert db.get("id50")["n"] == 950 and db.query(vecs[950], top_k=1)[0][K_ID] == "id50"
+    # a bad item at position 280 (second block): the flushed first block and the 24 staged items are committed
+    more = [{K_VECTOR: vecs[n + i], K_ID: f"new{i}"} for i in range(300)]
+    more[280] = {K_VECTOR: np.zeros(3, np.float32), K_ID: "bad"}
+    with pytest.raises(ValueError, match="dim mismatch"):
+        db.upsert(more)
+    assert len(db) == 900 + 280 and db.get("new279") is not None and db.get("new280") is None
+    assert db.query(vecs[n + 279], top_k=1)[0][K_ID] == "new279"
+    assert db.query(vecs[n + 123], top_k=1)[0][K_ID] == "new123"
+
+
 def test_stored_vector_is_normalised(make_db):
     # reference tests/test_more.py:236-260 and tests/test_memmap_capacity.py:42-47
     db = make_db(dim=2)
