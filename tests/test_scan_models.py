@@ -8,6 +8,8 @@ The kernels themselves are checked against the oracle in tests/test_gpu_parity.p
   * the reduce-scatter of the several-queries kernel: V = NQ * R partial sums over LPR lanes; lane `sub` ends with
     the totals of values (top << (LV - NS)) | j, and every total is the butterfly's sum (same additions).
   * sparse_walk: every set bit of (active & prefilter) is scored exactly once, in full steps except the last.
+  * scan_mma_topk_kernel: the three-term bf16 split carries an fp32 query exactly, and the "k index is only a
+    label" operand mapping of mma.sync.m16n8k16 (one and two queries per pass) yields whole-row dot products.
 """
 import numpy as np
 import pytest
@@ -138,3 +140,69 @@ def test_sparse_walk_visits_every_live_row_once_in_full_steps(rpw, density):
         assert all(len(s) == rpw for s in steps[:-1]), "only a warp's last step may run partly empty"
         visited += [r for s in steps for r in s]
     assert sorted(visited) == np.flatnonzero(bits).tolist()
+
+
+# ------------------------------------------------------------------ the mma.sync scan's operand mapping
+def _bf16_rn(x):
+    """fp32 -> bf16 (round to nearest even) -> fp32, as __float2bfloat16_rn."""
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def test_three_bf16_terms_carry_an_fp32_query_exactly():
+    """q = hi + mid + lo with three bf16 terms (8 + 8 + 8 mantissa bits): exact for unit-vector components."""
+    x = np.random.default_rng(0).standard_normal(100_000).astype(np.float32) / np.float32(20.0)
+    hi = _bf16_rn(x)
+    r1 = (x - hi).astype(np.float32)
+    mid = _bf16_rn(r1)
+    r2 = (r1 - mid).astype(np.float32)
+    lo = _bf16_rn(r2)
+    np.testing.assert_array_equal(((lo.astype(np.float64) + mid) + hi), x.astype(np.float64))
+
+
+@pytest.mark.parametrize("nq", [1, 2])
+def test_mma_fragment_mapping_scores_whole_rows(nq):
+    """scan_mma_topk_kernel feeds mma.sync.m16n8k16 with 16-byte row chunks as they lie in memory: thread
+    (g, t) loads columns [8t, 8t + 8) of rows g and g + 8 of a 32-column slice and hands .x/.y to one MMA and
+    .z/.w to a second one, so the instruction's k index is only a LABEL for a column -- the same relabelling
+    on the query side (B operand) makes C[row, n] the dot product of the row's 16 columns with part n.
+    B columns: part g % 3 of query g / 3 (0-2: the lone query; 3-5: the second query of a pair).  The model
+    walks the PTX fragment layout lane by lane and checks the scores the kernel extracts (thread t == 0: first
+    query, t == 1: second) against float64 dot products of the three-term split."""
+    rng = np.random.default_rng(nq)
+    rows = _bf16_rn(rng.standard_normal((16, 32)).astype(np.float32))          # one warp step, one 32-column slice
+    q = (rng.standard_normal((nq, 32)) / 6).astype(np.float32)
+    parts = np.zeros((8, 32), np.float32)                                      # B column n -> its 32 query values
+    for qi in range(nq):
+        hi = _bf16_rn(q[qi])
+        mid = _bf16_rn((q[qi] - hi).astype(np.float32))
+        lo = _bf16_rn(((q[qi] - hi).astype(np.float32) - mid).astype(np.float32))
+        parts[3 * qi + 0], parts[3 * qi + 1], parts[3 * qi + 2] = hi, mid, lo
+    # PTX m16n8k16 fragments of thread (g, t): A a0 = (row g, k 2t..2t+1), a1 = (row g+8, same k),
+    # a2 = (row g, k 2t+8..2t+9), a3 = (row g+8, same); B b0 = (k 2t..2t+1, col g), b1 = (k 2t+8..2t+9, col g);
+    # C c0,c1 = (row g, cols 2t, 2t+1), c2,c3 = (row g+8, cols 2t, 2t+1).
+    C = np.zeros((16, 8), np.float64)
+    for half in (0, 1):                       # ca: words .x/.y (columns 8t .. 8t+3), cb: .z/.w (8t+4 .. 8t+7)
+        A = np.zeros((16, 16))
+        B = np.zeros((16, 8))
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            cols = [8 * t + 4 * half + j for j in range(4)]          # this thread's four columns for this MMA
+            for r in (g, g + 8):
+                A[r, 2 * t], A[r, 2 * t + 1] = rows[r, cols[0]], rows[r, cols[1]]          # a0 / a1
+                A[r, 2 * t + 8], A[r, 2 * t + 9] = rows[r, cols[2]], rows[r, cols[3]]      # a2 / a3
+            B[2 * t, g], B[2 * t + 1, g] = parts[g, cols[0]], parts[g, cols[1]]            # b0 (bq[ks][2 half])
+            B[2 * t + 8, g], B[2 * t + 9, g] = parts[g, cols[2]], parts[g, cols[3]]        # b1 (bq[ks][2 half + 1])
+        C += A @ B
+    want = rows.astype(np.float64) @ parts.astype(np.float64).T
+    np.testing.assert_allclose(C, want, rtol=0, atol=1e-12)
+    # what the lanes hold and how the kernel combines it: (lo + mid) + hi
+    for g in range(8):
+        for r in (g, g + 8):
+            c = {t: (C[r, 2 * t], C[r, 2 * t + 1]) for t in range(4)}
+            s0 = (c[1][0] + c[0][1]) + c[0][0]                        # t == 0: lo from lane + 1
+            assert abs(s0 - rows[r].astype(np.float64) @ q[0].astype(np.float64)) < 1e-12
+            if nq == 2:
+                s1 = (c[2][1] + c[2][0]) + c[1][1]                    # t == 1: (mid, lo) from lane + 1
+                assert abs(s1 - rows[r].astype(np.float64) @ q[1].astype(np.float64)) < 1e-12
